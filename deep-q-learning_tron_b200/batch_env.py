@@ -1,0 +1,286 @@
+"""BatchedTron -- the vectorised batch API: N independent 2-player TRON games stepped in lockstep on one GPU.
+
+Semantics follow the reference one game at a time (tron/game.py:149-277 Game.next_frame/step,
+tron/map.py:67-84 state_for_player, tron/util.py:11-37 pop_up, tron/util.py:46-84 make_game,
+ACKTR.py:285-317 auto-reset).  All compute happens in libtron_b200.so through the C ABI; torch only
+owns the device memory and supplies the stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _abi as abi
+from . import _lib
+
+_TORCH_OF = {abi.BF16: torch.bfloat16, abi.F32: torch.float32, abi.I8: torch.int8}
+_CODE_OF = {torch.bfloat16: abi.BF16, torch.float32: abi.F32, torch.int8: abi.I8, torch.uint8: abi.U8,
+            torch.int32: abi.I32, torch.int64: abi.I64}
+_ENC_OF = {"none": abi.ENC_NONE, "lut1": abi.ENC_LUT1, "popup3": abi.ENC_POPUP3, "popup3_const": abi.ENC_POPUP3_CONST}
+_SLIDE_OF = {None: abi.SLIDE_NONE, "tape": abi.SLIDE_TAPE, "ice": abi.SLIDE_ICE, "temper": abi.SLIDE_TEMPER}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class StepResult(tuple):
+    """(obs, reward, done, winner, ep_len) with attribute access."""
+    __slots__ = ()
+    obs = property(lambda s: s[0])
+    reward = property(lambda s: s[1])
+    done = property(lambda s: s[2])
+    winner = property(lambda s: s[3])
+    ep_len = property(lambda s: s[4])
+
+
+class BatchedTron:
+    """N games of width x height on `device`.
+
+    obs layout: [N, 2, P, width+2, height+2]; obs[:, p] is player p+1's NCHW view (zero-copy).
+    reward: name in abi.REWARD_POLICIES or a 5-tuple (step_base, step_per_tick, win, lose, draw).
+    """
+
+    def __init__(self, n_envs, width=10, height=10, device="cuda", obs_dtype=torch.bfloat16, obs_enc="lut1", lut=None,
+                 const_plane=0.0, reward="ddqn", auto_reset=True, seed=0, env_id_base=0, slide_mode=None,
+                 slide_rate=0.15, collect_stats=True):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.TronError("BatchedTron needs a CUDA device; there is no CPU fallback")
+        self.N, self.W, self.H = int(n_envs), int(width), int(height)
+        self.C = abi.cells_per_env(width, height)
+        self.obs_enc = _ENC_OF[obs_enc] if isinstance(obs_enc, str) else int(obs_enc)
+        self.P = abi.enc_planes(self.obs_enc)
+        self.obs_dtype = obs_dtype if isinstance(obs_dtype, int) else _CODE_OF[obs_dtype]
+        self.lut = tuple(lut) if lut is not None else (0,) * 6
+        self.const_plane = float(const_plane)
+        self.reward_table = abi.Reward(*(abi.REWARD_POLICIES[reward] if isinstance(reward, str) else reward))
+        self.auto_reset = bool(auto_reset)
+        self.seed, self.env_id_base = int(seed), int(env_id_base)
+        self.slide_mode = _SLIDE_OF[slide_mode] if (slide_mode is None or isinstance(slide_mode, str)) else int(slide_mode)
+        self.slide_rate = float(slide_rate)
+        self.counter = 0
+        nbytes = C.c_size_t()
+        _lib.check(self.lib.tron_state_bytes(self.N, self.W, self.H, abi.LAYOUT_TILE8, C.byref(nbytes)), "tron_state_bytes")
+        with torch.cuda.device(self.device):
+            self.state = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
+            self.stats = torch.zeros(abi.STATS_SLOTS * abi.STATS_FIELDS, dtype=torch.int64, device=self.device) if collect_stats else None
+            self.slide_params = (torch.zeros((self.N, 4), dtype=torch.int8, device=self.device)
+                                 if self.slide_mode == abi.SLIDE_TEMPER else None)
+
+    # ------------------------------------------------------------------ buffers
+    def new_obs(self, ticks=None):
+        shape = (self.N, 2, self.P, self.W + 2, self.H + 2)
+        if ticks is not None:
+            shape = (ticks,) + shape
+        return torch.empty(shape, dtype=_TORCH_OF[self.obs_dtype], device=self.device)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _args(self, **kw):
+        a = abi.new_step_args(n_envs=self.N, width=self.W, height=self.H, layout=abi.LAYOUT_TILE8, state=self.state.data_ptr(),
+                              obs_dtype=self.obs_dtype, obs_enc=self.obs_enc, lut=self.lut, const_plane=self.const_plane,
+                              reward_table=self.reward_table, auto_reset=int(self.auto_reset), seed=self.seed,
+                              env_id_base=self.env_id_base, slide_mode=self.slide_mode, slide_rate=self.slide_rate,
+                              slide_params=_ptr(self.slide_params), stats=_ptr(self.stats))
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return a
+
+    def _dev(self, t, dtype):
+        if t is None:
+            return None
+        if not torch.is_tensor(t):
+            t = torch.as_tensor(t)
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    # ------------------------------------------------------------------ API
+    def reset(self, spawn=None, mask=None, obs=None, counter=None):
+        """Fresh games (Game.__init__).  spawn: [N,4] int8 {x1,y1,x2,y2} or None (RNG, make_game rule).
+        Returns the initial observation (or None for obs_enc='none')."""
+        if counter is None:
+            counter, self.counter = self.counter, self.counter + 1
+        sp = self._dev(spawn, torch.int8)
+        mk = self._dev(mask, torch.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tron_reset(self.state.data_ptr(), self.N, self.W, self.H, abi.LAYOUT_TILE8, _ptr(sp), _ptr(mk),
+                                           self.seed, counter, self.env_id_base, self._stream()), "tron_reset")
+        return self.observe(obs) if self.P else None
+
+    def observe(self, obs=None):
+        if obs is None:
+            obs = self.new_obs()
+        a = self._args(obs=obs.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tron_observe(C.byref(a), self._stream()), "tron_observe")
+        return obs
+
+    def step(self, actions=None, spawn=None, slide_tape=None, obs=None, reward=None, done=None, winner=None, ep_len=None,
+             counter=None, want_ep_len=True):
+        """One tick of every game.  actions: [N,2] uint8/int32/int64 tensor (P1,P2) or None (uniform random policy).
+        Output tensors may be passed in to avoid allocation.  -> StepResult(obs, reward, done, winner, ep_len)"""
+        if counter is None:
+            counter, self.counter = self.counter, self.counter + 1
+        N, dev = self.N, self.device
+        if actions is not None:
+            if not torch.is_tensor(actions):
+                actions = torch.as_tensor(actions)
+            if actions.device != dev or not actions.is_contiguous() or actions.dtype not in (torch.uint8, torch.int32, torch.int64):
+                actions = actions.to(device=dev, dtype=torch.uint8 if actions.dtype not in (torch.int32, torch.int64) else actions.dtype).contiguous()
+        sp = self._dev(spawn, torch.int8)
+        sl = self._dev(slide_tape, torch.uint8)
+        if obs is None and self.P:
+            obs = self.new_obs()
+        if reward is None:
+            reward = torch.empty((N, 2), dtype=torch.float32, device=dev)
+        if done is None:
+            done = torch.empty(N, dtype=torch.uint8, device=dev)
+        if winner is None:
+            winner = torch.empty(N, dtype=torch.uint8, device=dev)
+        if ep_len is None and want_ep_len:
+            ep_len = torch.empty(N, dtype=torch.int32, device=dev)
+        a = self._args(actions=_ptr(actions), action_dtype=0 if actions is None else _CODE_OF[actions.dtype], obs=_ptr(obs),
+                       reward=reward.data_ptr(), done=done.data_ptr(), winner=winner.data_ptr(), ep_len_out=_ptr(ep_len),
+                       spawn=_ptr(sp), slide_tape=_ptr(sl), counter=counter)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.tron_step(C.byref(a), self._stream()), "tron_step")
+        return StepResult((obs, reward, done, winner, ep_len))
+
+    def step_many(self, n_ticks, actions=None, spawn=None, obs_every_tick=True, counter=None):
+        """n_ticks ticks in one launch.  actions [T,N,2] or None (RNG), spawn [T,N,4] or None (RNG)."""
+        if counter is None:
+            counter, self.counter = self.counter, self.counter + n_ticks
+        T, N, dev = int(n_ticks), self.N, self.device
+        act = None
+        if actions is not None:
+            act = actions if torch.is_tensor(actions) else torch.as_tensor(actions)
+            dt = act.dtype if act.dtype in (torch.int32, torch.int64) else torch.uint8
+            act = act.to(device=dev, dtype=dt).contiguous()
+        sp = self._dev(spawn, torch.int8)
+        obs = (self.new_obs(T) if obs_every_tick else self.new_obs()) if self.P else None
+        reward = torch.empty((T, N, 2), dtype=torch.float32, device=dev)
+        done = torch.empty((T, N), dtype=torch.uint8, device=dev)
+        winner = torch.empty((T, N), dtype=torch.uint8, device=dev)
+        ep_len = torch.empty((T, N), dtype=torch.int32, device=dev)
+        a = self._args(actions=_ptr(act), action_dtype=0 if act is None else _CODE_OF[act.dtype], obs=_ptr(obs),
+                       reward=reward.data_ptr(), done=done.data_ptr(), winner=winner.data_ptr(), ep_len_out=ep_len.data_ptr(),
+                       spawn=_ptr(sp), counter=counter, n_ticks=T, obs_every_tick=int(obs_every_tick))
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.tron_step_many(C.byref(a), self._stream()), "tron_step_many")
+        return StepResult((obs, reward, done, winner, ep_len))
+
+    def export(self):
+        """Tile.value grids + per-player state as torch tensors (for history / shims / tests)."""
+        N, dev = self.N, self.device
+        out = dict(tiles=torch.empty((N, self.W + 2, self.H + 2), dtype=torch.int8, device=dev),
+                   heads=torch.empty((N, 4), dtype=torch.int8, device=dev), alive=torch.empty((N, 2), dtype=torch.uint8, device=dev),
+                   done=torch.empty(N, dtype=torch.uint8, device=dev), winner=torch.empty(N, dtype=torch.uint8, device=dev),
+                   ep_len=torch.empty(N, dtype=torch.int32, device=dev))
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.tron_export_grid(self.state.data_ptr(), N, self.W, self.H, abi.LAYOUT_TILE8, out["tiles"].data_ptr(),
+                                                 out["heads"].data_ptr(), out["alive"].data_ptr(), out["done"].data_ptr(),
+                                                 out["winner"].data_ptr(), out["ep_len"].data_ptr(), self._stream()), "tron_export_grid")
+        return out
+
+    def import_(self, tiles=None, heads=None, alive=None, done=None, winner=None, ep_len=None):
+        t = self._dev(tiles, torch.int8); h = self._dev(heads, torch.int8); al = self._dev(alive, torch.uint8)
+        d = self._dev(done, torch.uint8); w = self._dev(winner, torch.uint8); k = self._dev(ep_len, torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tron_import_grid(self.state.data_ptr(), self.N, self.W, self.H, abi.LAYOUT_TILE8, _ptr(t), _ptr(h),
+                                                 _ptr(al), _ptr(d), _ptr(w), _ptr(k), self._stream()), "tron_import_grid")
+
+    def random_actions(self, counter, out=None):
+        if out is None:
+            out = torch.empty((self.N, 2), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tron_random_actions(out.data_ptr(), self.N, self.seed, counter, self.env_id_base, self._stream()),
+                       "tron_random_actions")
+        return out
+
+    def select_actions(self, q, epsilon, counter, out=None):
+        """epsilon-greedy over q [N,2,4] or [2N,4] (float32/bfloat16) -> uint8 [N,2] (DDQN.py:90-110)."""
+        q2 = q.reshape(-1, 4).contiguous()
+        if out is None:
+            out = torch.empty(q2.shape[0], dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tron_select_actions(q2.data_ptr(), _CODE_OF[q2.dtype], q2.shape[0], float(epsilon), out.data_ptr(),
+                                                    self.seed, counter, 2 * self.env_id_base, self._stream()), "tron_select_actions")
+        return out.view(-1, 2) if out.numel() == 2 * self.N else out
+
+    def stats_dict(self):
+        """Summed on-device counters (episodes, wins, draws, ticks...).  Synchronises."""
+        if self.stats is None:
+            return {}
+        s = self.stats.view(abi.STATS_SLOTS, abi.STATS_FIELDS).sum(0).tolist()
+        return dict(episodes=s[abi.STAT_EPISODES], p1_wins=s[abi.STAT_P1_WINS], p2_wins=s[abi.STAT_P2_WINS], draws=s[abi.STAT_DRAWS],
+                    ep_ticks=s[abi.STAT_EP_TICKS], bad_action=s[abi.STAT_BAD_ACTION], env_steps=s[abi.STAT_ENV_STEPS])
+
+
+class HostTron:
+    """Host-buffer front end (tron_host_env_*): numpy in, numpy out, copies overlapped with the kernels."""
+
+    def __init__(self, n_envs, width=10, height=10, obs_dtype=abi.BF16, obs_enc=abi.ENC_LUT1, lut=None, const_plane=0.0,
+                 reward="ddqn", auto_reset=True, seed=0, env_id_base=0, n_chunks=8):
+        import numpy as np
+        _lib.require_cuda()
+        self.np = np
+        self.lib = _lib.load()
+        self.N, self.W, self.H = n_envs, width, height
+        self.P, self.obs_dtype = abi.enc_planes(obs_enc), obs_dtype
+        proto = abi.new_step_args(n_envs=n_envs, width=width, height=height, obs_dtype=obs_dtype, obs_enc=obs_enc,
+                                  lut=tuple(lut) if lut is not None else (0,) * 6, const_plane=const_plane,
+                                  reward_table=abi.REWARD_POLICIES[reward] if isinstance(reward, str) else reward,
+                                  auto_reset=int(auto_reset), seed=seed, env_id_base=env_id_base)
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.tron_host_env_create(C.byref(self.handle), C.byref(proto), n_chunks), "tron_host_env_create")
+        self._pinned = []
+        npdt = {abi.BF16: np.uint16, abi.F32: np.float32, abi.I8: np.int8}[obs_dtype]
+        self.obs = self.pinned((n_envs, 2, self.P, width + 2, height + 2), npdt) if self.P else None
+        self.actions = self.pinned((n_envs, 2), np.uint8)
+        self.reward = self.pinned((n_envs, 2), np.float32)
+        self.done = self.pinned((n_envs,), np.uint8)
+        self.winner = self.pinned((n_envs,), np.uint8)
+
+    def pinned(self, shape, dtype):
+        np = self.np
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        _lib.check(self.lib.tron_host_alloc(C.byref(p), nbytes), "tron_host_alloc")
+        self._pinned.append(p)
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def reset(self, spawn=None):
+        sp = None if spawn is None else self.np.ascontiguousarray(spawn, self.np.int8)
+        _lib.check(self.lib.tron_host_env_reset(self.handle, None if sp is None else sp.ctypes.data, None if self.obs is None else self.obs.ctypes.data),
+                   "tron_host_env_reset")
+        return self.obs
+
+    def step(self, actions=None, spawn=None):
+        if actions is not None:
+            self.actions[...] = actions
+        sp = None if spawn is None else self.np.ascontiguousarray(spawn, self.np.int8)
+        _lib.check(self.lib.tron_host_env_step(self.handle, self.actions.ctypes.data, None if sp is None else sp.ctypes.data,
+                                               None if self.obs is None else self.obs.ctypes.data, self.reward.ctypes.data,
+                                               self.done.ctypes.data, self.winner.ctypes.data), "tron_host_env_step")
+        return self.obs, self.reward, self.done, self.winner
+
+    def state_ptr(self):
+        return self.lib.tron_host_env_state(self.handle)
+
+    def close(self):
+        if self.handle:
+            self.lib.tron_host_env_destroy(self.handle)
+            self.handle = None
+        self.obs = self.actions = self.reward = self.done = self.winner = None
+        for p in self._pinned:
+            self.lib.tron_host_free(p)
+        self._pinned = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

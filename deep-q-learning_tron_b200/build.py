@@ -1,0 +1,61 @@
+"""Build libtron_b200.so (sm_100a only) in-tree with nvcc.  `python -m tron_b200.build` or build()."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIB = os.path.join(HERE, "libtron_b200.so")
+SOURCES = ["abi.cu", "step_c144.cu", "step_generic.cu", "misc_kernels.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+              "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    return os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+
+def _deps():
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(os.path.dirname(HERE), "include", "tron_b200.h"))
+    return hdrs
+
+
+def _stale(target, srcs):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    deps = _deps()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        if force or _stale(obj, [os.path.join(CSRC, src)] + deps):
+            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            with open(obj + ".log", "w") as f:
+                f.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr[-4000:]))
+            if verbose:
+                print(r.stderr[-2000:])
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    if force or _stale(LIB, objs):
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stderr[-4000:])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

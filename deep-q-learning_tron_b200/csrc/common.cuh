@@ -1,0 +1,113 @@
+// common.cuh -- device helpers shared by the TRON kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tron_b200.h"
+
+namespace tron {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG.  Counter = {tick counter (64b), stream id (48b) | tag | sub},
+// key = seed.  One stream per global env id, so results do not depend on how envs are sharded.
+// ---------------------------------------------------------------------------------------------
+enum : uint32_t { TAG_ACTION = 1, TAG_SPAWN = 2, TAG_SLIDE = 3, TAG_EPS = 4, TAG_SAMPLE = 5, TAG_TEMPER = 6 };
+
+__device__ __forceinline__ uint4 philox(unsigned long long seed, unsigned long long counter,
+                                        unsigned long long stream, uint32_t tag, uint32_t sub) {
+    uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = (uint32_t)stream;
+    uint32_t c3 = ((uint32_t)(stream >> 32) & 0xFFFFu) | ((tag & 0xFFu) << 16) | ((sub & 0xFFu) << 24);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// make_game spawn rule (reference tron/util.py:70-78): 4 uniform draws, re-draw only (x1,y1) while equal.
+__device__ __forceinline__ char4 rng_spawn(unsigned long long seed, unsigned long long counter,
+                                           unsigned long long env, int W, int H) {
+    uint4 r = philox(seed, counter, env, TAG_SPAWN, 0);
+    int x1 = (int)__umulhi(r.x, (uint32_t)W), y1 = (int)__umulhi(r.y, (uint32_t)H);
+    const int x2 = (int)__umulhi(r.z, (uint32_t)W), y2 = (int)__umulhi(r.w, (uint32_t)H);
+    uint32_t attempt = 0;
+    while (x1 == x2 && y1 == y2) {
+        if (++attempt >= 64) { x1 = (x2 + 1) % W; break; }
+        r = philox(seed, counter, env, TAG_SPAWN, attempt);
+        x1 = (int)__umulhi(r.x, (uint32_t)W); y1 = (int)__umulhi(r.y, (uint32_t)H);
+    }
+    return make_char4((signed char)x1, (signed char)y1, (signed char)x2, (signed char)y2);
+}
+
+// Game.__init__ draws (reference tron/game.py:83,87): weight x2 in [40,101], degree in [-30,30].
+__device__ __forceinline__ char4 rng_temper(unsigned long long seed, unsigned long long counter, unsigned long long env) {
+    const uint4 r = philox(seed, counter, env, TAG_TEMPER, 0);
+    return make_char4((signed char)(-30 + (int)__umulhi(r.z, 61u)), (signed char)(40 + (int)__umulhi(r.x, 62u)),
+                      (signed char)(40 + (int)__umulhi(r.y, 62u)), 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Blackwell/Hopper async-proxy helpers: 1-D bulk copies (TMA engine, no tensor map) + mbarrier.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_WAIT;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE_WAIT:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared, completion signalled on the mbarrier (bytes % 16 == 0, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// shared -> global, tracked by the per-thread bulk group
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// make generic-proxy shared-memory writes visible to the async proxy (before a bulk store reads them)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// streaming (evict-first) 16/8-byte global stores for write-once observation planes
+__device__ __forceinline__ void st_cs(uint4* p, uint4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_cs(uint2* p, uint2 v) { __stcs(p, v); }
+
+// ---------------------------------------------------------------------------------------------
+// Observation encoding: a cell byte (Tile.value, -1..6) indexes an 8-entry table by (tile & 7), so
+// WALL (-1) is entry 7.  Tables hold the bf16 bit pattern split into low/high bytes; PRMT looks up
+// four cells per instruction.  f32 = bf16 << 16 (every int8 is exact in bf16), i8 uses `lo` only.
+// ---------------------------------------------------------------------------------------------
+struct PlaneTab {  // 16 bytes
+    uint32_t lo0, lo1, hi0, hi1;
+};
+
+// selector for 4 cells packed in one 32-bit word: 4 nibbles = (cell & 7)
+__device__ __forceinline__ uint32_t cell_selector(uint32_t w) {
+    const uint32_t x = w & 0x07070707u;
+    const uint32_t t = x | (x >> 4);
+    return __byte_perm(t, 0u, 0x4420);
+}
+__device__ __forceinline__ uint32_t lut4(uint32_t t0, uint32_t t1, uint32_t sel) { return __byte_perm(t0, t1, sel); }
+
+}  // namespace tron

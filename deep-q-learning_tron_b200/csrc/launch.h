@@ -1,0 +1,35 @@
+// launch.h -- host-side launch entry points of the kernel translation units (internal, not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tron_b200.h"
+
+namespace tron {
+
+struct StepParams;
+
+__host__ __device__ inline int tron_elem(int dt) {
+    return (dt == TRON_U8 || dt == TRON_I8) ? 1 : dt == TRON_BF16 ? 2 : dt == TRON_I64 ? 8 : 4;
+}
+
+// step_c144.cu (10x10 grids, compile-time geometry) and step_generic.cu (any W,H)
+// enc_kind: 0 none, 1 = 1 lut plane, 2 = 3 lut planes, 3 = 3 lut planes + const plane
+int launch_step_c144(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
+int launch_step_generic(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
+int tile_envs_c144();
+int tile_envs_generic(int cells);
+
+int launch_export_meta(const void* meta, int n, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner, int32_t* ep_len, cudaStream_t s);
+int launch_import_meta(void* meta, int n, const int8_t* heads, const uint8_t* alive, const uint8_t* done, const uint8_t* winner,
+                       const int32_t* ep_len, cudaStream_t s);
+int launch_random_actions(uint8_t* actions, int n, uint64_t seed, uint64_t counter, uint64_t base, cudaStream_t s);
+int launch_select_actions(const void* q, int q_dtype, int n, float eps, uint8_t* actions, uint64_t seed, uint64_t counter, uint64_t base,
+                          cudaStream_t s);
+int launch_replay_push(const replay_ring* ring, uint64_t cursor, const void* s, const void* s2, const uint8_t* action, const float* reward,
+                       const uint8_t* done, int done_stride, int64_t n, cudaStream_t st);
+int launch_replay_gather(const replay_ring* ring, const int64_t* idx, int64_t k, void* out_s, void* out_s2, int out_dtype, int64_t* out_a,
+                         float* out_r, float* out_d, cudaStream_t st);
+int launch_replay_sample(int64_t size, int k, uint64_t seed, uint64_t counter, int64_t* idx, cudaStream_t st);
+
+}  // namespace tron

@@ -1,0 +1,55 @@
+// step_dispatch.cuh -- instantiates step_tile_kernel for one geometry class and dispatches at run time.
+#pragma once
+#include "launch.h"
+#include "step_kernels.cuh"
+
+namespace tron {
+
+constexpr int kThreads = 128;
+
+inline size_t tile_smem_bytes(int G, int C) {
+    return (size_t)((G * C + 15) & ~15) + (size_t)((C + 15) & ~15) + (size_t)G * 4 + (size_t)G + 8 + 16;
+}
+
+template <int C_T, int OD, int LP, bool CP, int CH, int MODE>
+int launch_one(const StepParams& p, cudaStream_t s) {
+    auto kern = step_tile_kernel<C_T, kThreads, OD, LP, CP, CH, MODE>;
+    const size_t smem = tile_smem_bytes(p.G, p.C);
+    static size_t smem_limit = 48 * 1024;  // raised lazily; per instantiation
+    if (smem > smem_limit) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TRON_ERR_CUDA;
+        smem_limit = smem;
+    }
+    const unsigned grid = (unsigned)(((long long)p.N + p.G - 1) / p.G);
+    kern<<<grid, kThreads, smem, s>>>(p);
+    return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
+}
+
+template <int C_T, int OD, int CH, int MODE>
+int launch_enc(const StepParams& p, int enc_kind, cudaStream_t s) {
+    switch (enc_kind) {
+        case 1: return launch_one<C_T, OD, 1, false, CH, MODE>(p, s);
+        case 2: return launch_one<C_T, OD, 3, false, CH, MODE>(p, s);
+        case 3: return launch_one<C_T, OD, 3, true, CH, MODE>(p, s);
+        default: return TRON_ERR_INVALID;
+    }
+}
+
+template <int C_T, int CH>
+int launch_mode(const StepParams& p, int mode, int od, int enc_kind, cudaStream_t s) {
+    if (mode == MODE_RESET) return launch_one<C_T, TRON_I8, 0, false, CH, MODE_RESET>(p, s);
+    if (mode == MODE_STEP && enc_kind == 0) return launch_one<C_T, TRON_I8, 0, false, CH, MODE_STEP>(p, s);
+    if (enc_kind == 0) return TRON_ERR_INVALID;
+    if (mode == MODE_STEP) {
+        if (od == TRON_BF16) return launch_enc<C_T, TRON_BF16, CH, MODE_STEP>(p, enc_kind, s);
+        if (od == TRON_F32) return launch_enc<C_T, TRON_F32, CH, MODE_STEP>(p, enc_kind, s);
+        if (od == TRON_I8) return launch_enc<C_T, TRON_I8, CH, MODE_STEP>(p, enc_kind, s);
+    } else if (mode == MODE_OBSERVE) {
+        if (od == TRON_BF16) return launch_enc<C_T, TRON_BF16, CH, MODE_OBSERVE>(p, enc_kind, s);
+        if (od == TRON_F32) return launch_enc<C_T, TRON_F32, CH, MODE_OBSERVE>(p, enc_kind, s);
+        if (od == TRON_I8) return launch_enc<C_T, TRON_I8, CH, MODE_OBSERVE>(p, enc_kind, s);
+    }
+    return TRON_ERR_INVALID;
+}
+
+}  // namespace tron

@@ -226,6 +226,13 @@ int tron_select_actions(const void* q, int q_dtype, int n_rows, float epsilon, u
     return launch_select_actions(q, q_dtype, n_rows, epsilon, actions, seed, counter, row_id_base, (cudaStream_t)stream);
 }
 
+int tron_pop_up(const void* obs, int obs_dtype, int64_t n_maps, int cells, void* planes, int out_dtype, tron_stream_t stream) {
+    if (!obs || !planes || n_maps <= 0 || cells <= 0) return TRON_ERR_INVALID;
+    if (obs_dtype != TRON_F32 && obs_dtype != TRON_BF16 && obs_dtype != TRON_I8 && obs_dtype != TRON_I32 && obs_dtype != TRON_I64) return TRON_ERR_INVALID;
+    if (out_dtype != TRON_F32 && out_dtype != TRON_BF16 && out_dtype != TRON_I8) return TRON_ERR_INVALID;
+    return launch_pop_up(obs, obs_dtype, n_maps, cells, planes, out_dtype, (cudaStream_t)stream);
+}
+
 static int ring_ok(const replay_ring* r) {
     if (!r || r->struct_size != sizeof(replay_ring) || r->capacity <= 0 || r->frame_elems <= 0) return 0;
     if (r->frame_dtype != TRON_BF16 && r->frame_dtype != TRON_F32 && r->frame_dtype != TRON_I8) return 0;

@@ -26,6 +26,7 @@ int launch_import_meta(void* meta, int n, const int8_t* heads, const uint8_t* al
 int launch_random_actions(uint8_t* actions, int n, uint64_t seed, uint64_t counter, uint64_t base, cudaStream_t s);
 int launch_select_actions(const void* q, int q_dtype, int n, float eps, uint8_t* actions, uint64_t seed, uint64_t counter, uint64_t base,
                           cudaStream_t s);
+int launch_pop_up(const void* obs, int in_dtype, int64_t n_maps, int cells, void* planes, int out_dtype, cudaStream_t s);
 int launch_replay_push(const replay_ring* ring, uint64_t cursor, const void* s, const void* s2, const uint8_t* action, const float* reward,
                        const uint8_t* done, int done_stride, int64_t n, cudaStream_t st);
 int launch_replay_gather(const replay_ring* ring, const int64_t* idx, int64_t k, void* out_s, void* out_s2, int out_dtype, int64_t* out_a,

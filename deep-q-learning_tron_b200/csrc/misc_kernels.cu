@@ -95,6 +95,36 @@ int launch_select_actions(const void* q, int q_dtype, int n, float eps, uint8_t*
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 
+// pop_up (reference tron/util.py:11-37) on already-encoded observations: [n, cells] -> [n, 3, cells] planes
+// wall = (o == -1); my = 1 if o == -2, 10 if o == 10; enemy = 1 if o == -3, 10 if o == -10.
+__global__ void pop_up_kernel(const void* __restrict__ obs, int in_dtype, long long n_maps, int cells, void* planes, int out_dtype) {
+    const long long total = n_maps * cells;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float o;
+        if (in_dtype == TRON_F32) o = ((const float*)obs)[i];
+        else if (in_dtype == TRON_BF16) o = __uint_as_float((uint32_t)((const uint16_t*)obs)[i] << 16);
+        else if (in_dtype == TRON_I8) o = (float)((const int8_t*)obs)[i];
+        else if (in_dtype == TRON_I32) o = (float)((const int32_t*)obs)[i];
+        else o = (float)((const long long*)obs)[i];
+        const float w = o == -1.f ? 1.f : 0.f;
+        const float m = o == -2.f ? 1.f : o == 10.f ? 10.f : 0.f;
+        const float e = o == -3.f ? 1.f : o == -10.f ? 10.f : 0.f;
+        const long long map = i / cells, c = i - map * cells;
+        const long long b = map * 3 * cells + c;
+        if (out_dtype == TRON_F32) { ((float*)planes)[b] = w; ((float*)planes)[b + cells] = m; ((float*)planes)[b + 2 * cells] = e; }
+        else if (out_dtype == TRON_BF16) {
+            ((__nv_bfloat16*)planes)[b] = __float2bfloat16_rn(w); ((__nv_bfloat16*)planes)[b + cells] = __float2bfloat16_rn(m);
+            ((__nv_bfloat16*)planes)[b + 2 * cells] = __float2bfloat16_rn(e);
+        } else { ((int8_t*)planes)[b] = (int8_t)w; ((int8_t*)planes)[b + cells] = (int8_t)m; ((int8_t*)planes)[b + 2 * cells] = (int8_t)e; }
+    }
+}
+int launch_pop_up(const void* obs, int in_dtype, int64_t n_maps, int cells, void* planes, int out_dtype, cudaStream_t s) {
+    const long long total = n_maps * cells;
+    const int blocks = (int)min((long long)148 * 16, (total + 255) / 256);
+    pop_up_kernel<<<blocks, 256, 0, s>>>(obs, in_dtype, n_maps, cells, planes, out_dtype);
+    return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
+}
+
 // ------------------------------------------------------------------------------------------------
 // replay ring.  A batched step yields 2N transitions whose frames are already contiguous
 // ([N,2,P,C] == [2N, frame]), so push is a wrapped streaming copy and gather a row gather.

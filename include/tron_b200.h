@@ -214,6 +214,12 @@ int tron_random_actions(uint8_t* actions, int n_envs, uint64_t seed, uint64_t co
 int tron_select_actions(const void* q, int q_dtype, int n_rows, float epsilon, uint8_t* actions,
                         uint64_t seed, uint64_t counter, uint64_t row_id_base, tron_stream_t stream);
 
+/* pop_up on observations that are already encoded (reference tron/util.py:11-37): obs device [n_maps, cells]
+ * (TRON_I8|TRON_I32|TRON_I64|TRON_BF16|TRON_F32) -> planes device [n_maps, 3, cells] = {wall, my, enemy}
+ * (TRON_F32|TRON_BF16|TRON_I8).  The fused path (TRON_ENC_POPUP3) never materialises the 1-plane form. */
+int tron_pop_up(const void* obs, int obs_dtype, int64_t n_maps, int cells, void* planes, int out_dtype,
+                tron_stream_t stream);
+
 /* ---- replay ring (DQN.py:81-132 ReplayMemory, DDQN.py:167-203 ReplayBuffer) ---- */
 typedef struct replay_ring {
     uint32_t struct_size;

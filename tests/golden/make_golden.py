@@ -37,6 +37,8 @@ def import_reference():
                 "    def add(self, x): self[x] = None\n"
                 "    def remove(self, x): del self[x]\n"
                 "    def __getitem__(self, i): return list(self.keys())[i]\n")
+    for m in [k for k in sys.modules if k.split(".")[0] in ("tron", "config", "DQN", "DDQN", "Net")]:
+        del sys.modules[m]  # never mix the reference's modules with the drop-in mirrors of the same names
     sys.path.insert(0, shim)
     sys.path.insert(0, REF)
     import tron.game as game  # noqa

@@ -17,6 +17,7 @@ U8, I32, I64, BF16, F32, I8 = 0, 1, 2, 3, 4, 5
 # encodings
 ENC_NONE, ENC_LUT1, ENC_POPUP3, ENC_POPUP3_CONST = 0, 1, 2, 3
 LAYOUT_TILE8 = 0
+OPT_SPARSE_MIN_CELLS = 1
 SLIDE_NONE, SLIDE_TAPE, SLIDE_ICE, SLIDE_TEMPER = 0, 1, 2, 3
 STATS_SLOTS, STATS_FIELDS = 64, 8
 (STAT_EPISODES, STAT_P1_WINS, STAT_P2_WINS, STAT_DRAWS, STAT_EP_TICKS, STAT_BAD_ACTION,
@@ -98,14 +99,15 @@ def dtype_size(dt):
 
 def state_bytes(n_envs, width, height):
     grid = (n_envs * cells_per_env(width, height) + 255) & ~255
-    return grid + 8 * n_envs
+    meta = (8 * n_envs + 255) & ~255
+    return grid + meta + 8 * n_envs
 
 
 # Every symbol the header declares; tests check that the built library exports each one.
 EXPORTED_SYMBOLS = (
     "tron_abi_version", "tron_status_string", "tron_device_count",
     "tron_state_bytes", "tron_state_offsets", "tron_cells_per_env", "tron_enc_planes",
-    "tron_dtype_size", "tron_build_plane_tables",
+    "tron_dtype_size", "tron_build_plane_tables", "tron_set_option",
     "tron_reset", "tron_step", "tron_observe", "tron_step_many", "tron_export_grid",
     "tron_import_grid", "tron_random_actions", "tron_select_actions", "tron_pop_up",
     "replay_push", "replay_gather", "replay_sample_indices",

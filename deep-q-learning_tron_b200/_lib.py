@@ -23,7 +23,8 @@ _SIGS = {
     "tron_status_string": (C.c_char_p, [_i]),
     "tron_device_count": (C.c_int, []),
     "tron_state_bytes": (C.c_int, [_i, _i, _i, _i, C.POINTER(C.c_size_t)]),
-    "tron_state_offsets": (C.c_int, [_i, _i, _i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "tron_state_offsets": (C.c_int, [_i, _i, _i, _i, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    "tron_set_option": (C.c_int, [_i, _i64]),
     "tron_cells_per_env": (C.c_int, [_i, _i]),
     "tron_enc_planes": (C.c_int, [_i]),
     "tron_dtype_size": (C.c_int, [_i]),

@@ -52,6 +52,7 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
     p.N = a->n_envs; p.W = a->width; p.H = a->height; p.Hc = a->height + 2; p.C = (a->width + 2) * (a->height + 2);
     p.grid = (int8_t*)a->state;
     p.meta = (uint2*)((char*)a->state + align256((size_t)p.N * p.C));
+    p.boxes = (uint2*)((char*)p.meta + align256((size_t)p.N * sizeof(tron_meta)));
     p.T = 1; p.obs_every_tick = 1;
     const int planes = planes_of(a->obs_enc);
     if (a->obs_enc != TRON_ENC_NONE) {
@@ -80,8 +81,11 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
     return TRON_OK;
 }
 
+long long g_sparse_min_cells = 1024;  // TRON_OPT_SPARSE_MIN_CELLS
+
 int dispatch(StepParams& p, int mode, int obs_dtype, int obs_enc, cudaStream_t s) {
     const int kind = enc_kind_of(obs_enc);
+    if (mode == MODE_STEP && kind == 0 && p.C >= g_sparse_min_cells) return launch_step_sparse(p, s);
     if (p.C == 144 && p.Hc == 12) { p.G = tile_envs_c144(); return launch_step_c144(p, mode, obs_dtype, kind, s); }
     p.G = tile_envs_generic(p.C);
     return launch_step_generic(p, mode, obs_dtype, kind, s);
@@ -114,18 +118,24 @@ int tron_cells_per_env(int width, int height) { return (width + 2) * (height + 2
 int tron_enc_planes(int obs_enc) { return planes_of(obs_enc); }
 int tron_dtype_size(int dtype) { return tron_elem(dtype); }
 
-int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* grid_off, size_t* meta_off) {
+int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* grid_off, size_t* meta_off, size_t* boxes_off) {
     if (!geometry_ok(n_envs, width, height) || layout != TRON_LAYOUT_TILE8) return TRON_ERR_INVALID;
+    const size_t mo = align256((size_t)n_envs * (size_t)tron_cells_per_env(width, height));
     if (grid_off) *grid_off = 0;
-    if (meta_off) *meta_off = align256((size_t)n_envs * (size_t)tron_cells_per_env(width, height));
+    if (meta_off) *meta_off = mo;
+    if (boxes_off) *boxes_off = mo + align256((size_t)n_envs * sizeof(tron_meta));
     return TRON_OK;
 }
 int tron_state_bytes(int n_envs, int width, int height, int layout, size_t* total_bytes) {
-    size_t mo = 0;
-    const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo);
+    size_t bo = 0;
+    const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, nullptr, &bo);
     if (rc != TRON_OK || !total_bytes) return rc != TRON_OK ? rc : TRON_ERR_INVALID;
-    *total_bytes = mo + (size_t)n_envs * sizeof(tron_meta);
+    *total_bytes = bo + (size_t)n_envs * 8u;
     return TRON_OK;
+}
+int tron_set_option(int option, int64_t value) {
+    if (option == TRON_OPT_SPARSE_MIN_CELLS && value >= 0) { g_sparse_min_cells = value; return TRON_OK; }
+    return TRON_ERR_INVALID;
 }
 
 // reference tron/map.py:67-81 (colour table) and tron/util.py:11-37 (pop_up applied to the colour value)
@@ -195,7 +205,7 @@ int tron_observe(const tron_step_args* args, tron_stream_t stream) {
 int tron_export_grid(const void* state, int n_envs, int width, int height, int layout, int8_t* tiles, int8_t* heads,
                      uint8_t* alive, uint8_t* done, uint8_t* winner, int32_t* ep_len, tron_stream_t stream) {
     size_t mo = 0;
-    const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo);
+    const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo, nullptr);
     if (rc != TRON_OK || !state) return rc != TRON_OK ? rc : TRON_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     if (tiles && cudaMemcpyAsync(tiles, state, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
@@ -206,7 +216,7 @@ int tron_export_grid(const void* state, int n_envs, int width, int height, int l
 int tron_import_grid(void* state, int n_envs, int width, int height, int layout, const int8_t* tiles, const int8_t* heads,
                      const uint8_t* alive, const uint8_t* done, const uint8_t* winner, const int32_t* ep_len, tron_stream_t stream) {
     size_t mo = 0;
-    const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo);
+    const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo, nullptr);
     if (rc != TRON_OK || !state) return rc != TRON_OK ? rc : TRON_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
     if (tiles && cudaMemcpyAsync(state, tiles, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
@@ -344,7 +354,7 @@ static int host_env_run(tron_host_env* e, int mode, const uint8_t* actions_h, co
         if (spawn_h) ok = ok && cudaMemcpyAsync(e->d_spawn + 4 * (size_t)lo, spawn_h + 4 * (size_t)lo, 4 * (size_t)n, cudaMemcpyHostToDevice, s) == cudaSuccess;
         StepParams p = base;
         p.N = n; p.env_base = base.env_base + (unsigned long long)lo;
-        p.grid = base.grid + (size_t)lo * C; p.meta = base.meta + lo;
+        p.grid = base.grid + (size_t)lo * C; p.meta = base.meta + lo; p.boxes = base.boxes + lo;
         if (p.actions) p.actions = (const uint8_t*)base.actions + 2 * (size_t)lo;
         if (p.spawn) p.spawn = base.spawn + 4 * (size_t)lo;
         if (p.obs) p.obs = (char*)base.obs + (size_t)lo * frame;

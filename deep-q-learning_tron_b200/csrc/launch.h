@@ -17,6 +17,7 @@ __host__ __device__ inline int tron_elem(int dt) {
 // enc_kind: 0 none, 1 = 1 lut plane, 2 = 3 lut planes, 3 = 3 lut planes + const plane
 int launch_step_c144(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_step_generic(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
+int launch_step_sparse(const StepParams& p, cudaStream_t s);
 int tile_envs_c144();
 int tile_envs_generic(int cells);
 

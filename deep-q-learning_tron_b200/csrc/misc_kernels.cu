@@ -34,6 +34,7 @@ __global__ void import_meta_kernel(uint2* __restrict__ meta, int n, const int8_t
     if (done) f = (f & ~TRON_FLAG_DONE) | (done[e] ? TRON_FLAG_DONE : 0u);
     if (winner) f = (f & ~(3u << TRON_FLAG_WINNER_SHIFT)) | ((winner[e] & 3u) << TRON_FLAG_WINNER_SHIFT);
     if (ep_len) k = (uint32_t)ep_len[e] & 0xFFFFu;
+    f &= ~0x20u;  // TRON_FLAG_BOXES_VALID: an imported grid has unknown dirty boxes
     m.y = f | (k << 16);
     meta[e] = m;
 }

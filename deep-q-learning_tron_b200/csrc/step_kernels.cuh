@@ -12,40 +12,9 @@
 // HBM traffic per game-tick: C read + C written (grid) + 2*P*C*sizeof(obs) written + ~30 B metadata.
 #pragma once
 #include "common.cuh"
+#include "tick_core.cuh"
 
 namespace tron {
-
-enum : int { MODE_STEP = 0, MODE_OBSERVE = 1, MODE_RESET = 2 };
-
-struct StepParams {
-    int8_t* grid;
-    uint2* meta;  // tron_meta, 8 bytes
-    const void* actions;
-    void* obs;
-    float* reward;
-    uint8_t* done;
-    uint8_t* winner;
-    int32_t* eplen;
-    const int8_t* spawn;
-    const uint8_t* slide_tape;
-    int8_t* slide_params;
-    const uint8_t* env_mask;  // MODE_RESET
-    unsigned long long* stats;
-    unsigned long long seed, counter, env_base;
-    long long ice_thr;
-    int N, W, H, Hc, C, G;
-    int T, obs_every_tick, auto_reset, slide_mode, action_dtype;
-    int P;  // planes written per player (lut planes + optional const plane)
-    float r_base, r_tick, r_win, r_lose, r_draw, const_plane;
-    PlaneTab tab[2][3];
-};
-
-__device__ __forceinline__ int read_action(const void* actions, int dtype, size_t i) {
-    if (dtype == TRON_U8) return ((const uint8_t*)actions)[i];
-    if (dtype == TRON_I32) { const int v = ((const int32_t*)actions)[i]; return (v < 0 || v > 255) ? 255 : v; }
-    const long long v = ((const long long*)actions)[i];
-    return (v < 0 || v > 255) ? 255 : (int)v;
-}
 
 // ---- observation element packing --------------------------------------------------------------
 // 4 cells -> 4 encoded elements of dtype OD, returned as raw 32-bit words (1 word i8, 2 bf16, 4 f32)
@@ -144,135 +113,17 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
     for (int t = 0; t < T; ++t) {
         if (MODE != MODE_OBSERVE) {
             // ------------------------------------------------------------ phase 1: thread-per-game tick
-            bool do_reset = false;
             if (owner) {
-                int r1 = (int8_t)(mraw.x & 0xFF), c1 = (int8_t)((mraw.x >> 8) & 0xFF), r2 = (int8_t)((mraw.x >> 16) & 0xFF),
-                    c2 = (int8_t)(mraw.x >> 24);
-                uint32_t flags = mraw.y & 0xFFu;
-                int k = (int)(mraw.y >> 16);
-                const unsigned long long genv = p.env_base + (unsigned long long)env;
-                const unsigned long long ctr = p.counter + (unsigned long long)t;
-                const size_t tn = (size_t)t * (size_t)p.N + (size_t)env;
-                char4 sp = make_char4(0, 0, 0, 0);
-                if (MODE == MODE_RESET) {
-                    do_reset = p.env_mask ? p.env_mask[env] != 0 : true;
-                } else {
-                    int a1, a2;
-                    if (p.actions) {
-                        a1 = read_action(p.actions, p.action_dtype, 2 * tn);
-                        a2 = read_action(p.actions, p.action_dtype, 2 * tn + 1);
-                    } else {
-                        const uint4 r = philox(p.seed, ctr, genv, TAG_ACTION, 0);
-                        a1 = (int)(r.x >> 30); a2 = (int)(r.y >> 30);
-                    }
-                    float rw0 = 0.f, rw1 = 0.f;
-                    uint32_t done = 0, winner = 0;
-                    int fin = 0;
-                    bool bad = false, stepped = false;
-                    if (flags & TRON_FLAG_DONE) {  // finished game without auto-reset stays frozen
-                        done = 1; winner = (flags >> TRON_FLAG_WINNER_SHIFT) & 3u;
-                    } else if (a1 > 3 || a2 > 3) {
-                        bad = true;
-                    } else {
-                        stepped = true;
-                        int8_t* g = tile + tid * C;
-                        const int Hc = p.Hc;
-                        // reference game.py:155-156: both old heads become bodies before any move
-                        g[(r1 + 1) * Hc + c1 + 1] = TRON_TILE_P1_BODY;
-                        g[(r2 + 1) * Hc + c2 + 1] = TRON_TILE_P2_BODY;
-                        // reference player.py:124-132
-                        const int dr1 = (a1 == 2) - (a1 == 0), dc1 = (a1 == 1) - (a1 == 3);
-                        const int dr2 = (a2 == 2) - (a2 == 0), dc2 = (a2 == 1) - (a2 == 3);
-                        r1 += dr1; c1 += dc1;
-                        if (p.slide_mode != TRON_SLIDE_NONE) {  // reference game.py:163-178
-                            uint4 sr = make_uint4(0, 0, 0, 0);
-                            if (p.slide_mode >= TRON_SLIDE_ICE) sr = philox(p.seed, ctr, genv, TAG_SLIDE, 0);
-                            char4 tp = make_char4(0, 0, 0, 0);
-                            if (p.slide_mode == TRON_SLIDE_TEMPER) tp = ((const char4*)p.slide_params)[env];
-#pragma unroll
-                            for (int i = 0; i < 2; ++i) {
-                                int& rr = i ? r2 : r1; int& cc = i ? c2 : c1;
-                                const int dr = i ? dr2 : dr1, dc = i ? dc2 : dc1;
-                                if (i) { rr += dr; cc += dc; }
-                                if (rr >= 0 && cc >= 0 && rr < p.W && cc < p.H && g[(rr + 1) * Hc + cc + 1] == TRON_TILE_EMPTY) {
-                                    bool slip;
-                                    const long long mant = (long long)((i ? sr.y : sr.x) >> 8);
-                                    if (p.slide_mode == TRON_SLIDE_TAPE) slip = p.slide_tape[2 * tn + i] != 0;
-                                    else if (p.slide_mode == TRON_SLIDE_ICE) slip = mant <= p.ice_thr;
-                                    else {
-                                        const long long K = 6 * (30 - (long long)tp.x) - 700 + 10 * (long long)(i ? tp.z : tp.y);
-                                        slip = mant * 1000 <= K * 16777216;
-                                    }
-                                    if (slip) {
-                                        g[(rr + 1) * Hc + cc + 1] = i ? TRON_TILE_P2_SLIDE : TRON_TILE_P1_SLIDE;
-                                        rr += dr; cc += dc;
-                                    }
-                                }
-                            }
-                        } else {
-                            r2 += dr2; c2 += dc2;
-                        }
-                        // reference game.py:205-214: P1 fully resolved before P2, head written in every case
-                        bool al1 = flags & TRON_FLAG_ALIVE1, al2 = flags & TRON_FLAG_ALIVE2;
-                        const int i1 = (r1 + 1) * Hc + c1 + 1;
-                        if (r1 < 0 || c1 < 0 || r1 >= p.W || c1 >= p.H || g[i1] != TRON_TILE_EMPTY) al1 = false;
-                        g[i1] = TRON_TILE_P1_HEAD;
-                        const int i2 = (r2 + 1) * Hc + c2 + 1;
-                        if (r2 < 0 || c2 < 0 || r2 >= p.W || c2 >= p.H || g[i2] != TRON_TILE_EMPTY) al2 = false;
-                        g[i2] = TRON_TILE_P2_HEAD;
-                        // reference game.py:264-277
-                        const int n_alive = (int)al1 + (int)al2;
-                        if (n_alive <= 1) {
-                            done = 1;
-                            if (n_alive == 1 && (r1 != r2 || c1 != c2)) winner = al1 ? 1u : 2u;
-                        }
-                        flags = (al1 ? TRON_FLAG_ALIVE1 : 0u) | (al2 ? TRON_FLAG_ALIVE2 : 0u) | (done ? TRON_FLAG_DONE : 0u) |
-                                (winner << TRON_FLAG_WINNER_SHIFT);
-                        if (!done) {
-                            rw0 = rw1 = p.r_base + p.r_tick * (float)k;
-                        } else {
-                            if (winner == 0) rw0 = rw1 = p.r_draw;
-                            else { rw0 = winner == 1 ? p.r_win : p.r_lose; rw1 = winner == 2 ? p.r_win : p.r_lose; }
-                            fin = k + 1;
-                            do_reset = p.auto_reset != 0;
-                        }
-                        k += 1;
-                    }
-                    if (p.reward) ((float2*)p.reward)[tn] = make_float2(rw0, rw1);
-                    if (p.done) p.done[tn] = (uint8_t)done;
-                    if (p.winner) p.winner[tn] = (uint8_t)winner;
-                    if (p.eplen) p.eplen[tn] = fin;
-                    if (p.stats) {  // warp-aggregated counters, striped over TRON_STATS_SLOTS rows
-                        const unsigned am = __activemask();
-                        const unsigned m_fin = __ballot_sync(am, fin > 0), m_w1 = __ballot_sync(am, fin > 0 && winner == 1),
-                                       m_w2 = __ballot_sync(am, fin > 0 && winner == 2), m_bad = __ballot_sync(am, bad),
-                                       m_step = __ballot_sync(am, stepped);
-                        const unsigned ticks = __reduce_add_sync(am, (unsigned)fin);
-                        if ((tid & 31) == (__ffs(am) - 1)) {
-                            unsigned long long* s = p.stats + (size_t)(blockIdx.x % TRON_STATS_SLOTS) * TRON_STATS_FIELDS;
-                            if (m_fin) {
-                                atomicAdd(s + TRON_STAT_EPISODES, (unsigned long long)__popc(m_fin));
-                                atomicAdd(s + TRON_STAT_P1_WINS, (unsigned long long)__popc(m_w1));
-                                atomicAdd(s + TRON_STAT_P2_WINS, (unsigned long long)__popc(m_w2));
-                                atomicAdd(s + TRON_STAT_DRAWS, (unsigned long long)(__popc(m_fin) - __popc(m_w1) - __popc(m_w2)));
-                                atomicAdd(s + TRON_STAT_EP_TICKS, (unsigned long long)ticks);
-                            }
-                            if (m_bad) atomicAdd(s + TRON_STAT_BAD_ACTION, (unsigned long long)__popc(m_bad));
-                            atomicAdd(s + TRON_STAT_ENV_STEPS, (unsigned long long)__popc(m_step));
-                        }
-                    }
+                EnvState e = unpack_meta(mraw);
+                BoxRegs bx;
+                const bool do_reset = env_tick<MODE, false>(tile + tid * C, p, e, env, t, tid, bx);
+                if (MODE == MODE_RESET && do_reset && p.boxes) {  // a fresh grid has exactly two non-template cells
+                    box_set_spawn(bx, e);
+                    p.boxes[env] = pack_boxes(bx);
+                    e.flags |= TRON_FLAG_BOXES_VALID;
                 }
-                if (do_reset) {  // fresh game (reference game.py:70-91, util.py:70-78)
-                    if (p.spawn) sp = ((const char4*)p.spawn)[tn];
-                    else sp = rng_spawn(p.seed, ctr, genv, p.W, p.H);
-                    r1 = sp.x; c1 = sp.y; r2 = sp.z; c2 = sp.w;
-                    flags = TRON_FLAG_ALIVE1 | TRON_FLAG_ALIVE2; k = 0;
-                    hidx[tid] = make_ushort2((unsigned short)((r1 + 1) * p.Hc + c1 + 1), (unsigned short)((r2 + 1) * p.Hc + c2 + 1));
-                    if (MODE == MODE_STEP && p.slide_mode == TRON_SLIDE_TEMPER && p.slide_params)
-                        ((char4*)p.slide_params)[env] = rng_temper(p.seed, ctr, genv);
-                }
-                mraw.x = (uint32_t)(uint8_t)r1 | ((uint32_t)(uint8_t)c1 << 8) | ((uint32_t)(uint8_t)r2 << 16) | ((uint32_t)(uint8_t)c2 << 24);
-                mraw.y = flags | ((uint32_t)k << 16);
+                if (do_reset) hidx[tid] = make_ushort2((unsigned short)((e.r1 + 1) * p.Hc + e.c1 + 1), (unsigned short)((e.r2 + 1) * p.Hc + e.c2 + 1));
+                mraw = pack_meta(e);
                 rflag[tid] = do_reset ? 1 : 0;
             }
             __syncthreads();

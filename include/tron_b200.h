@@ -76,7 +76,7 @@ enum {
 };
 
 /* state layouts */
-enum { TRON_LAYOUT_TILE8 = 0 /* int8 Tile.value per cell + 8-byte meta per env */ };
+enum { TRON_LAYOUT_TILE8 = 0 /* int8 Tile.value per cell + 8-byte meta + 8-byte dirty boxes per env */ };
 
 /* slide ("ice"/"temper") modes, tron/game.py:163-178 */
 enum {
@@ -89,7 +89,7 @@ enum {
 /* Per-env metadata, 8 bytes, stored after the grids inside the state blob. */
 typedef struct tron_meta {
     int8_t r1, c1, r2, c2; /* head positions [p0,p1] of player 1 and 2; range -1..W / -1..H */
-    uint8_t flags;         /* bit0 P1 alive, bit1 P2 alive, bit2 done, bits3-4 winner (0 none,1,2) */
+    uint8_t flags;         /* bit0 P1 alive, bit1 P2 alive, bit2 done, bits3-4 winner (0 none,1,2), bit5 dirty boxes valid */
     uint8_t reserved;
     uint16_t ep_len;       /* ticks played in the current episode (len(game.history)-1) */
 } tron_meta;
@@ -175,7 +175,12 @@ int tron_device_count(void);
 /* ---- geometry helpers (host only, no CUDA call) ---- */
 /* Bytes of the state blob for N envs; cells per env; planes for an encoding; element size of a dtype. */
 int tron_state_bytes(int n_envs, int width, int height, int layout, size_t* total_bytes);
-int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* grid_off, size_t* meta_off);
+int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* grid_off, size_t* meta_off,
+                       size_t* boxes_off);
+/* Tuning knobs (process-wide).  TRON_OPT_SPARSE_MIN_CELLS: pure ticks (TRON_ENC_NONE) of games with at least this
+ * many cells run thread-per-game on HBM with dirty-box resets instead of staging whole grids (default 1024). */
+enum { TRON_OPT_SPARSE_MIN_CELLS = 1 };
+int tron_set_option(int option, int64_t value);
 int tron_cells_per_env(int width, int height);
 int tron_enc_planes(int obs_enc);
 int tron_dtype_size(int dtype);

@@ -37,16 +37,19 @@ int launch_enc(const StepParams& p, int enc_kind, cudaStream_t s) {
 
 template <int C_T, int CH>
 int launch_mode(const StepParams& p, int mode, int od, int enc_kind, cudaStream_t s) {
+    // f32 planes: 4 cells per item so that one warp-wide STG.128 covers whole 32-byte sectors (8 cells would give each
+    // lane two half-sector stores; measured 78% -> see profiles/r1_step_f32_lut1_2M.json)
+    constexpr int CH32 = CH == 8 ? 4 : CH;
     if (mode == MODE_RESET) return launch_one<C_T, TRON_I8, 0, false, CH, MODE_RESET>(p, s);
     if (mode == MODE_STEP && enc_kind == 0) return launch_one<C_T, TRON_I8, 0, false, CH, MODE_STEP>(p, s);
     if (enc_kind == 0) return TRON_ERR_INVALID;
     if (mode == MODE_STEP) {
         if (od == TRON_BF16) return launch_enc<C_T, TRON_BF16, CH, MODE_STEP>(p, enc_kind, s);
-        if (od == TRON_F32) return launch_enc<C_T, TRON_F32, CH, MODE_STEP>(p, enc_kind, s);
+        if (od == TRON_F32) return launch_enc<C_T, TRON_F32, CH32, MODE_STEP>(p, enc_kind, s);
         if (od == TRON_I8) return launch_enc<C_T, TRON_I8, CH, MODE_STEP>(p, enc_kind, s);
     } else if (mode == MODE_OBSERVE) {
         if (od == TRON_BF16) return launch_enc<C_T, TRON_BF16, CH, MODE_OBSERVE>(p, enc_kind, s);
-        if (od == TRON_F32) return launch_enc<C_T, TRON_F32, CH, MODE_OBSERVE>(p, enc_kind, s);
+        if (od == TRON_F32) return launch_enc<C_T, TRON_F32, CH32, MODE_OBSERVE>(p, enc_kind, s);
         if (od == TRON_I8) return launch_enc<C_T, TRON_I8, CH, MODE_OBSERVE>(p, enc_kind, s);
     }
     return TRON_ERR_INVALID;

@@ -1,0 +1,12 @@
+#!/usr/bin/env python
+"""Run one sweep case for a few steps (to be wrapped by ncu).  usage: profile_case.py <envs> <grid> <dtype> <enc> [steps]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from sweep import run  # noqa: E402
+
+if __name__ == "__main__":
+    n, w, dt, enc = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
+    steps = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+    run("profile", n, w, dt, enc, steps=steps, warmup=2)

@@ -54,7 +54,7 @@ def run(name, N, W, dtype, enc, steps=20, warmup=3, actions="tape", auto_reset=T
     return out
 
 
-if __name__ == "__main__":
+def main():
     quick = "--quick" in sys.argv
     M = 1 << 20
     run("10x10 bf16 1-plane (headline)", 4 * M, 10, "bf16", "lut1")
@@ -70,3 +70,7 @@ if __name__ == "__main__":
         run("10x10 bf16, 65,536 envs (config #3 size)", 65536, 10, "bf16", "popup3", steps=200)
         run("10x10 bf16, 4,096 envs (config #2 size, launch-bound)", 4096, 10, "bf16", "lut1", steps=500)
         run("32x32 bf16 1-plane", 512 * 1024, 32, "bf16", "lut1", steps=10)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,7 @@ U8, I32, I64, BF16, F32, I8 = 0, 1, 2, 3, 4, 5
 # encodings
 ENC_NONE, ENC_LUT1, ENC_POPUP3, ENC_POPUP3_CONST = 0, 1, 2, 3
 LAYOUT_TILE8 = 0
+LAYOUT_BITS10 = 1
 OPT_SPARSE_MIN_CELLS = 1
 SLIDE_NONE, SLIDE_TAPE, SLIDE_ICE, SLIDE_TEMPER = 0, 1, 2, 3
 STATS_SLOTS, STATS_FIELDS = 64, 8
@@ -97,8 +98,9 @@ def dtype_size(dt):
     return {U8: 1, I8: 1, BF16: 2, I32: 4, F32: 4, I64: 8}[dt]
 
 
-def state_bytes(n_envs, width, height):
-    grid = (n_envs * cells_per_env(width, height) + 255) & ~255
+def state_bytes(n_envs, width, height, layout=LAYOUT_TILE8):
+    per = 32 if layout == LAYOUT_BITS10 else cells_per_env(width, height)
+    grid = (n_envs * per + 255) & ~255
     meta = (8 * n_envs + 255) & ~255
     return grid + meta + 8 * n_envs
 

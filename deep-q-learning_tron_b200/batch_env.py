@@ -16,6 +16,7 @@ _TORCH_OF = {abi.BF16: torch.bfloat16, abi.F32: torch.float32, abi.I8: torch.int
 _CODE_OF = {torch.bfloat16: abi.BF16, torch.float32: abi.F32, torch.int8: abi.I8, torch.uint8: abi.U8,
             torch.int32: abi.I32, torch.int64: abi.I64}
 _ENC_OF = {"none": abi.ENC_NONE, "lut1": abi.ENC_LUT1, "popup3": abi.ENC_POPUP3, "popup3_const": abi.ENC_POPUP3_CONST}
+_LAYOUT_OF = {"tile8": abi.LAYOUT_TILE8, "bits10": abi.LAYOUT_BITS10}
 _SLIDE_OF = {None: abi.SLIDE_NONE, "tape": abi.SLIDE_TAPE, "ice": abi.SLIDE_ICE, "temper": abi.SLIDE_TEMPER}
 
 
@@ -42,9 +43,10 @@ class BatchedTron:
 
     def __init__(self, n_envs, width=10, height=10, device="cuda", obs_dtype=torch.bfloat16, obs_enc="lut1", lut=None,
                  const_plane=0.0, reward="ddqn", auto_reset=True, seed=0, env_id_base=0, slide_mode=None,
-                 slide_rate=0.15, collect_stats=True):
+                 slide_rate=0.15, collect_stats=True, layout="tile8"):
         _lib.require_cuda()
         self.lib = _lib.load()
+        self.layout = _LAYOUT_OF[layout] if isinstance(layout, str) else int(layout)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.TronError("BatchedTron needs a CUDA device; there is no CPU fallback")
@@ -62,7 +64,7 @@ class BatchedTron:
         self.slide_rate = float(slide_rate)
         self.counter = 0
         nbytes = C.c_size_t()
-        _lib.check(self.lib.tron_state_bytes(self.N, self.W, self.H, abi.LAYOUT_TILE8, C.byref(nbytes)), "tron_state_bytes")
+        _lib.check(self.lib.tron_state_bytes(self.N, self.W, self.H, self.layout, C.byref(nbytes)), "tron_state_bytes")
         with torch.cuda.device(self.device):
             self.state = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
             self.stats = torch.zeros(abi.STATS_SLOTS * abi.STATS_FIELDS, dtype=torch.int64, device=self.device) if collect_stats else None
@@ -80,7 +82,7 @@ class BatchedTron:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _args(self, **kw):
-        a = abi.new_step_args(n_envs=self.N, width=self.W, height=self.H, layout=abi.LAYOUT_TILE8, state=self.state.data_ptr(),
+        a = abi.new_step_args(n_envs=self.N, width=self.W, height=self.H, layout=self.layout, state=self.state.data_ptr(),
                               obs_dtype=self.obs_dtype, obs_enc=self.obs_enc, lut=self.lut, const_plane=self.const_plane,
                               reward_table=self.reward_table, auto_reset=int(self.auto_reset), seed=self.seed,
                               env_id_base=self.env_id_base, slide_mode=self.slide_mode, slide_rate=self.slide_rate,
@@ -105,7 +107,7 @@ class BatchedTron:
         sp = self._dev(spawn, torch.int8)
         mk = self._dev(mask, torch.uint8)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tron_reset(self.state.data_ptr(), self.N, self.W, self.H, abi.LAYOUT_TILE8, _ptr(sp), _ptr(mk),
+            _lib.check(self.lib.tron_reset(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(sp), _ptr(mk),
                                            self.seed, counter, self.env_id_base, self._stream()), "tron_reset")
         return self.observe(obs) if self.P else None
 
@@ -179,7 +181,7 @@ class BatchedTron:
                    done=torch.empty(N, dtype=torch.uint8, device=dev), winner=torch.empty(N, dtype=torch.uint8, device=dev),
                    ep_len=torch.empty(N, dtype=torch.int32, device=dev))
         with torch.cuda.device(dev):
-            _lib.check(self.lib.tron_export_grid(self.state.data_ptr(), N, self.W, self.H, abi.LAYOUT_TILE8, out["tiles"].data_ptr(),
+            _lib.check(self.lib.tron_export_grid(self.state.data_ptr(), N, self.W, self.H, self.layout, out["tiles"].data_ptr(),
                                                  out["heads"].data_ptr(), out["alive"].data_ptr(), out["done"].data_ptr(),
                                                  out["winner"].data_ptr(), out["ep_len"].data_ptr(), self._stream()), "tron_export_grid")
         return out
@@ -188,7 +190,7 @@ class BatchedTron:
         t = self._dev(tiles, torch.int8); h = self._dev(heads, torch.int8); al = self._dev(alive, torch.uint8)
         d = self._dev(done, torch.uint8); w = self._dev(winner, torch.uint8); k = self._dev(ep_len, torch.int32)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tron_import_grid(self.state.data_ptr(), self.N, self.W, self.H, abi.LAYOUT_TILE8, _ptr(t), _ptr(h),
+            _lib.check(self.lib.tron_import_grid(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(t), _ptr(h),
                                                  _ptr(al), _ptr(d), _ptr(w), _ptr(k), self._stream()), "tron_import_grid")
 
     def random_actions(self, counter, out=None):
@@ -222,7 +224,7 @@ class HostTron:
     """Host-buffer front end (tron_host_env_*): numpy in, numpy out, copies overlapped with the kernels."""
 
     def __init__(self, n_envs, width=10, height=10, obs_dtype=abi.BF16, obs_enc=abi.ENC_LUT1, lut=None, const_plane=0.0,
-                 reward="ddqn", auto_reset=True, seed=0, env_id_base=0, n_chunks=8):
+                 reward="ddqn", auto_reset=True, seed=0, env_id_base=0, n_chunks=8, layout="tile8"):
         import numpy as np
         _lib.require_cuda()
         self.np = np
@@ -230,6 +232,7 @@ class HostTron:
         self.N, self.W, self.H = n_envs, width, height
         self.P, self.obs_dtype = abi.enc_planes(obs_enc), obs_dtype
         proto = abi.new_step_args(n_envs=n_envs, width=width, height=height, obs_dtype=obs_dtype, obs_enc=obs_enc,
+                                  layout=_LAYOUT_OF[layout] if isinstance(layout, str) else int(layout),
                                   lut=tuple(lut) if lut is not None else (0,) * 6, const_plane=const_plane,
                                   reward_table=abi.REWARD_POLICIES[reward] if isinstance(reward, str) else reward,
                                   auto_reset=int(auto_reset), seed=seed, env_id_base=env_id_base)

@@ -14,6 +14,9 @@ namespace {
 
 inline size_t align256(size_t x) { return (x + 255u) & ~(size_t)255u; }
 inline bool geometry_ok(int n, int w, int h) { return n > 0 && w >= 2 && h >= 2 && w <= 126 && h <= 126; }
+inline bool layout_ok(int layout, int w, int h) { return layout == TRON_LAYOUT_TILE8 || (layout == TRON_LAYOUT_BITS10 && w == 10 && h == 10); }
+// bytes of grid state per game
+inline size_t grid_stride(int layout, int w, int h) { return layout == TRON_LAYOUT_BITS10 ? 32u : (size_t)(w + 2) * (size_t)(h + 2); }
 inline int planes_of(int enc) { return enc == TRON_ENC_LUT1 ? 1 : enc == TRON_ENC_POPUP3 ? 3 : enc == TRON_ENC_POPUP3_CONST ? 4 : 0; }
 inline int enc_kind_of(int enc) { return enc == TRON_ENC_LUT1 ? 1 : enc == TRON_ENC_POPUP3 ? 2 : enc == TRON_ENC_POPUP3_CONST ? 3 : 0; }
 
@@ -46,12 +49,16 @@ void build_device_tables(const int8_t lut6[6], int enc, int obs_dtype, PlaneTab 
 // Fill kernel parameters from the public argument block.  grid/meta may be overridden (chunked host path).
 int fill_params(const tron_step_args* a, int mode, StepParams& p) {
     if (!a || a->struct_size != sizeof(tron_step_args)) return TRON_ERR_INVALID;
-    if (!geometry_ok(a->n_envs, a->width, a->height) || a->layout != TRON_LAYOUT_TILE8 || !a->state) return TRON_ERR_INVALID;
+    if (!geometry_ok(a->n_envs, a->width, a->height) || !a->state) return TRON_ERR_INVALID;
+    if (a->layout != TRON_LAYOUT_TILE8 && a->layout != TRON_LAYOUT_BITS10) return TRON_ERR_INVALID;
+    if (!layout_ok(a->layout, a->width, a->height)) return TRON_ERR_UNSUPPORTED;
+    if (a->layout == TRON_LAYOUT_BITS10 && mode == MODE_STEP && a->slide_mode != TRON_SLIDE_NONE) return TRON_ERR_UNSUPPORTED;
     if (((uintptr_t)a->state & 15u) != 0) return TRON_ERR_ALIGN;
     memset(&p, 0, sizeof p);
     p.N = a->n_envs; p.W = a->width; p.H = a->height; p.Hc = a->height + 2; p.C = (a->width + 2) * (a->height + 2);
+    p.layout = a->layout;
     p.grid = (int8_t*)a->state;
-    p.meta = (uint2*)((char*)a->state + align256((size_t)p.N * p.C));
+    p.meta = (uint2*)((char*)a->state + align256((size_t)p.N * grid_stride(a->layout, a->width, a->height)));
     p.boxes = (uint2*)((char*)p.meta + align256((size_t)p.N * sizeof(tron_meta)));
     p.T = 1; p.obs_every_tick = 1;
     const int planes = planes_of(a->obs_enc);
@@ -85,6 +92,7 @@ long long g_sparse_min_cells = 1024;  // TRON_OPT_SPARSE_MIN_CELLS
 
 int dispatch(StepParams& p, int mode, int obs_dtype, int obs_enc, cudaStream_t s) {
     const int kind = enc_kind_of(obs_enc);
+    if (p.layout == TRON_LAYOUT_BITS10) return launch_step_bits10(p, mode, obs_dtype, kind, s);
     if (mode == MODE_STEP && kind == 0 && p.C >= g_sparse_min_cells) return launch_step_sparse(p, s);
     if (p.C == 144 && p.Hc == 12) { p.G = tile_envs_c144(); return launch_step_c144(p, mode, obs_dtype, kind, s); }
     p.G = tile_envs_generic(p.C);
@@ -119,8 +127,9 @@ int tron_enc_planes(int obs_enc) { return planes_of(obs_enc); }
 int tron_dtype_size(int dtype) { return tron_elem(dtype); }
 
 int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* grid_off, size_t* meta_off, size_t* boxes_off) {
-    if (!geometry_ok(n_envs, width, height) || layout != TRON_LAYOUT_TILE8) return TRON_ERR_INVALID;
-    const size_t mo = align256((size_t)n_envs * (size_t)tron_cells_per_env(width, height));
+    if (!geometry_ok(n_envs, width, height) || (layout != TRON_LAYOUT_TILE8 && layout != TRON_LAYOUT_BITS10)) return TRON_ERR_INVALID;
+    if (!layout_ok(layout, width, height)) return TRON_ERR_UNSUPPORTED;
+    const size_t mo = align256((size_t)n_envs * grid_stride(layout, width, height));
     if (grid_off) *grid_off = 0;
     if (meta_off) *meta_off = mo;
     if (boxes_off) *boxes_off = mo + align256((size_t)n_envs * sizeof(tron_meta));
@@ -208,8 +217,11 @@ int tron_export_grid(const void* state, int n_envs, int width, int height, int l
     const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo, nullptr);
     if (rc != TRON_OK || !state) return rc != TRON_OK ? rc : TRON_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
-    if (tiles && cudaMemcpyAsync(tiles, state, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    if (tiles && layout == TRON_LAYOUT_BITS10) {
+        if (launch_bits10_export(state, (const char*)state + mo, n_envs, tiles, s) != TRON_OK) return TRON_ERR_CUDA;
+    } else if (tiles && cudaMemcpyAsync(tiles, state, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
         return TRON_ERR_CUDA;
+    }
     return launch_export_meta((const char*)state + mo, n_envs, heads, alive, done, winner, ep_len, s);
 }
 
@@ -219,8 +231,11 @@ int tron_import_grid(void* state, int n_envs, int width, int height, int layout,
     const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo, nullptr);
     if (rc != TRON_OK || !state) return rc != TRON_OK ? rc : TRON_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
-    if (tiles && cudaMemcpyAsync(state, tiles, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    if (tiles && layout == TRON_LAYOUT_BITS10) {
+        if (launch_bits10_import(state, n_envs, tiles, s) != TRON_OK) return TRON_ERR_CUDA;
+    } else if (tiles && cudaMemcpyAsync(state, tiles, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
         return TRON_ERR_CUDA;
+    }
     return launch_import_meta((char*)state + mo, n_envs, heads, alive, done, winner, ep_len, s);
 }
 
@@ -312,7 +327,7 @@ int tron_host_env_create(tron_host_env** out, const tron_step_args* proto, int n
     e->counter = 0;
     const size_t N = (size_t)proto->n_envs;
     size_t sb = 0;
-    tron_state_bytes(proto->n_envs, proto->width, proto->height, TRON_LAYOUT_TILE8, &sb);
+    if (tron_state_bytes(proto->n_envs, proto->width, proto->height, proto->layout, &sb) != TRON_OK) { delete e; return TRON_ERR_UNSUPPORTED; }
     bool ok = cudaMalloc(&e->d_state, sb) == cudaSuccess && cudaMalloc((void**)&e->d_actions, N * 2) == cudaSuccess &&
               cudaMalloc((void**)&e->d_spawn, N * 4) == cudaSuccess && cudaMalloc((void**)&e->d_reward, N * 8) == cudaSuccess &&
               cudaMalloc((void**)&e->d_done, N) == cudaSuccess && cudaMalloc((void**)&e->d_winner, N) == cudaSuccess;
@@ -354,7 +369,7 @@ static int host_env_run(tron_host_env* e, int mode, const uint8_t* actions_h, co
         if (spawn_h) ok = ok && cudaMemcpyAsync(e->d_spawn + 4 * (size_t)lo, spawn_h + 4 * (size_t)lo, 4 * (size_t)n, cudaMemcpyHostToDevice, s) == cudaSuccess;
         StepParams p = base;
         p.N = n; p.env_base = base.env_base + (unsigned long long)lo;
-        p.grid = base.grid + (size_t)lo * C; p.meta = base.meta + lo; p.boxes = base.boxes + lo;
+        p.grid = base.grid + (size_t)lo * grid_stride(base.layout, base.W, base.H); p.meta = base.meta + lo; p.boxes = base.boxes + lo;
         if (p.actions) p.actions = (const uint8_t*)base.actions + 2 * (size_t)lo;
         if (p.spawn) p.spawn = base.spawn + 4 * (size_t)lo;
         if (p.obs) p.obs = (char*)base.obs + (size_t)lo * frame;

@@ -18,6 +18,9 @@ __host__ __device__ inline int tron_elem(int dt) {
 int launch_step_c144(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_step_generic(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_step_sparse(const StepParams& p, cudaStream_t s);
+int launch_step_bits10(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
+int launch_bits10_export(const void* planes, const void* meta, int n, int8_t* tiles, cudaStream_t s);
+int launch_bits10_import(void* planes, int n, const int8_t* tiles, cudaStream_t s);
 int tile_envs_c144();
 int tile_envs_generic(int cells);
 

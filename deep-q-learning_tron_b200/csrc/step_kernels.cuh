@@ -58,6 +58,61 @@ struct Enc4<TRON_I8> {
 template <int OD>
 __device__ __forceinline__ int elem_size() { return OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1; }
 
+// Encode both players' observation planes of a tile of nG games held in shared memory as int8 Tile.values.
+// Every warp-wide store covers whole 32-byte sectors; values come from 8-entry byte tables via PRMT (common.cuh).
+template <int C_T, int NT, int OD, int LP, bool CP, int CH>
+__device__ __forceinline__ void encode_tile(const int8_t* tile, int nG, long long env0, const StepParams& p, int t) {
+    const int C = C_T ? C_T : p.C;
+    const int tid = threadIdx.x;
+            constexpr int ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
+            const int P = p.P;
+            const size_t tick_off = (size_t)t * (size_t)p.N * 2 * (size_t)P * (size_t)C * ES;
+            char* obase = (char*)p.obs + tick_off;
+            if constexpr (CH >= 4) {
+                const int per = C / CH;
+                for (int it = tid; it < nG * per; it += NT) {
+                    const int e = it / per, ch = it - e * per;
+                    const int8_t* cells = tile + e * C + ch * CH;
+                    uint32_t sel[CH / 4];
+                    if constexpr (CH == 8) { const uint2 w = *(const uint2*)cells; sel[0] = cell_selector(w.x); sel[1] = cell_selector(w.y); }
+                    else { sel[0] = cell_selector(*(const uint32_t*)cells); }
+                    char* row0 = obase + ((size_t)(env0 + e) * 2 * P * C + (size_t)ch * CH) * ES;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+                        for (int q = 0; q < LP + (CP ? 1 : 0); ++q) {
+                            uint32_t o[(CH / 4) * Enc4<OD>::WORDS];
+#pragma unroll
+                            for (int h = 0; h < CH / 4; ++h) {
+                                if (q < LP) Enc4<OD>::run(p.tab[pl][q < LP ? q : 0], sel[h], o + h * Enc4<OD>::WORDS);
+                                else Enc4<OD>::fill(p.const_plane, o + h * Enc4<OD>::WORDS);
+                            }
+                            char* dst = row0 + (size_t)(pl * P + q) * C * ES;
+                            constexpr int NW = (CH / 4) * Enc4<OD>::WORDS;
+                            if (NW == 8) { st_cs((uint4*)dst, make_uint4(o[0], o[1], o[2], o[3])); st_cs((uint4*)dst + 1, make_uint4(o[4 % NW], o[5 % NW], o[6 % NW], o[7 % NW])); }
+                            else if (NW == 4) st_cs((uint4*)dst, make_uint4(o[0], o[1 % NW], o[2 % NW], o[3 % NW]));
+                            else if (NW == 2) st_cs((uint2*)dst, make_uint2(o[0], o[1 % NW]));
+                            else *(uint32_t*)dst = o[0];
+                        }
+                    }
+                }
+            } else {  // scalar fallback for odd cell counts
+                for (int it = tid; it < nG * C; it += NT) {
+                    const int e = it / C, c = it - e * C;
+                    const uint32_t sel = (uint32_t)tile[it] & 7u;
+                    for (int pl = 0; pl < 2; ++pl)
+                        for (int q = 0; q < LP + (CP ? 1 : 0); ++q) {
+                            uint32_t o[Enc4<OD>::WORDS];
+                            if (q < LP) Enc4<OD>::run(p.tab[pl][q < LP ? q : 0], sel, o); else Enc4<OD>::fill(p.const_plane, o);
+                            char* dst = obase + ((size_t)((env0 + e) * 2 + pl) * P + q) * C * ES + (size_t)c * ES;
+                            if (ES == 4) *(uint32_t*)dst = o[0];
+                            else if (ES == 2) *(uint16_t*)dst = (uint16_t)o[0];
+                            else *(uint8_t*)dst = (uint8_t)o[0];
+                        }
+                }
+            }
+        }
+
 // ---- the kernel -----------------------------------------------------------------------------
 // C_T: cells per env at compile time (0 = runtime), NT threads, OD obs dtype, LP lut planes (0 = no obs),
 // CP const plane, CH cells per encode item (8, 4 or 1; C % CH == 0), MODE.
@@ -116,7 +171,8 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
             if (owner) {
                 EnvState e = unpack_meta(mraw);
                 BoxRegs bx;
-                const bool do_reset = env_tick<MODE, false>(tile + tid * C, p, e, env, t, tid, bx);
+                ByteCells cells{tile + tid * C, p.Hc};
+                const bool do_reset = env_tick<MODE, false>(cells, p, e, env, t, tid, bx);
                 if (MODE == MODE_RESET && do_reset && p.boxes) {  // a fresh grid has exactly two non-template cells
                     box_set_spawn(bx, e);
                     p.boxes[env] = pack_boxes(bx);
@@ -164,55 +220,8 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
             }
         }
         // ---------------------------------------------------------------- phase 3: observation planes
-        if (LP > 0 && (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1)) {
-            constexpr int ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
-            const int P = p.P;
-            const size_t tick_off = (MODE == MODE_STEP && p.obs_every_tick) ? (size_t)t * (size_t)p.N * 2 * (size_t)P * (size_t)C * ES : 0;
-            char* obase = (char*)p.obs + tick_off;
-            if constexpr (CH >= 4) {
-                const int per = C / CH;
-                for (int it = tid; it < nG * per; it += NT) {
-                    const int e = it / per, ch = it - e * per;
-                    const int8_t* cells = tile + e * C + ch * CH;
-                    uint32_t sel[CH / 4];
-                    if constexpr (CH == 8) { const uint2 w = *(const uint2*)cells; sel[0] = cell_selector(w.x); sel[1] = cell_selector(w.y); }
-                    else { sel[0] = cell_selector(*(const uint32_t*)cells); }
-                    char* row0 = obase + ((size_t)(env0 + e) * 2 * P * C + (size_t)ch * CH) * ES;
-#pragma unroll
-                    for (int pl = 0; pl < 2; ++pl) {
-#pragma unroll
-                        for (int q = 0; q < LP + (CP ? 1 : 0); ++q) {
-                            uint32_t o[(CH / 4) * Enc4<OD>::WORDS];
-#pragma unroll
-                            for (int h = 0; h < CH / 4; ++h) {
-                                if (q < LP) Enc4<OD>::run(p.tab[pl][q < LP ? q : 0], sel[h], o + h * Enc4<OD>::WORDS);
-                                else Enc4<OD>::fill(p.const_plane, o + h * Enc4<OD>::WORDS);
-                            }
-                            char* dst = row0 + (size_t)(pl * P + q) * C * ES;
-                            constexpr int NW = (CH / 4) * Enc4<OD>::WORDS;
-                            if (NW == 8) { st_cs((uint4*)dst, make_uint4(o[0], o[1], o[2], o[3])); st_cs((uint4*)dst + 1, make_uint4(o[4 % NW], o[5 % NW], o[6 % NW], o[7 % NW])); }
-                            else if (NW == 4) st_cs((uint4*)dst, make_uint4(o[0], o[1 % NW], o[2 % NW], o[3 % NW]));
-                            else if (NW == 2) st_cs((uint2*)dst, make_uint2(o[0], o[1 % NW]));
-                            else *(uint32_t*)dst = o[0];
-                        }
-                    }
-                }
-            } else {  // scalar fallback for odd cell counts
-                for (int it = tid; it < nG * C; it += NT) {
-                    const int e = it / C, c = it - e * C;
-                    const uint32_t sel = (uint32_t)tile[it] & 7u;
-                    for (int pl = 0; pl < 2; ++pl)
-                        for (int q = 0; q < LP + (CP ? 1 : 0); ++q) {
-                            uint32_t o[Enc4<OD>::WORDS];
-                            if (q < LP) Enc4<OD>::run(p.tab[pl][q < LP ? q : 0], sel, o); else Enc4<OD>::fill(p.const_plane, o);
-                            char* dst = obase + ((size_t)((env0 + e) * 2 + pl) * P + q) * C * ES + (size_t)c * ES;
-                            if (ES == 4) *(uint32_t*)dst = o[0];
-                            else if (ES == 2) *(uint16_t*)dst = (uint16_t)o[0];
-                            else *(uint8_t*)dst = (uint8_t)o[0];
-                        }
-                }
-            }
-        }
+        if (LP > 0 && (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1))
+            encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, (MODE == MODE_STEP && p.obs_every_tick) ? t : 0);
         if (T > 1) __syncthreads();  // next tick's phase 1 rewrites the tile
     }
     if (MODE != MODE_OBSERVE && bulk_ok && tid == 0) bulk_wait_read_all();  // tile must outlive the bulk store's read

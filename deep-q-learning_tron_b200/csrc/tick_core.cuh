@@ -29,7 +29,7 @@ struct StepParams {
     unsigned long long* stats;
     unsigned long long seed, counter, env_base;
     long long ice_thr;
-    int N, W, H, Hc, C, G;
+    int N, W, H, Hc, C, G, layout;
     int T, obs_every_tick, auto_reset, slide_mode, action_dtype;
     int P;  // planes written per player (lut planes + optional const plane)
     float r_base, r_tick, r_win, r_lose, r_draw, const_plane;
@@ -81,10 +81,18 @@ __device__ __forceinline__ void box_set_spawn(BoxRegs& x, const EnvState& e) {
     x.lo_r[1] = x.hi_r[1] = e.r2; x.lo_c[1] = x.hi_c[1] = e.c2;
 }
 
+// Cell accessors: env_tick() is written against get(r,c)/put(r,c,tile) in POSITION coordinates (-1..W, -1..H).
+struct ByteCells {  // int8 Tile.value grid, row-major (W+2) x (H+2), in shared memory or HBM
+    int8_t* p;
+    int Hc;
+    __device__ __forceinline__ int get(int r, int c) const { return p[(r + 1) * Hc + c + 1]; }
+    __device__ __forceinline__ void put(int r, int c, int tile) { p[(r + 1) * Hc + c + 1] = (int8_t)tile; }
+};
+
 // One tick of the env whose cells start at `g`.  Updates `e` (fresh game state if it returns true = "rebuild this grid"),
 // writes reward/done/winner/ep_len for (tick t, env) and adds to the striped statistics.  TRACK maintains the dirty boxes.
-template <int MODE, bool TRACK>
-__device__ __forceinline__ bool env_tick(int8_t* g, const StepParams& p, EnvState& e, long long env, int t, int tid, BoxRegs& bx) {
+template <int MODE, bool TRACK, class Cells>
+__device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState& e, long long env, int t, int tid, BoxRegs& bx) {
     bool do_reset = false;
     const unsigned long long genv = p.env_base + (unsigned long long)env;
     const unsigned long long ctr = p.counter + (unsigned long long)t;
@@ -110,11 +118,10 @@ __device__ __forceinline__ bool env_tick(int8_t* g, const StepParams& p, EnvStat
             bad = true;
         } else {
             stepped = true;
-            const int Hc = p.Hc;
             int r1 = e.r1, c1 = e.c1, r2 = e.r2, c2 = e.c2;
             // reference game.py:155-156: both old heads become bodies before any move
-            g[(r1 + 1) * Hc + c1 + 1] = TRON_TILE_P1_BODY;
-            g[(r2 + 1) * Hc + c2 + 1] = TRON_TILE_P2_BODY;
+            g.put(r1, c1, TRON_TILE_P1_BODY);
+            g.put(r2, c2, TRON_TILE_P2_BODY);
             // reference player.py:124-132
             const int dr1 = (a1 == 2) - (a1 == 0), dc1 = (a1 == 1) - (a1 == 3);
             const int dr2 = (a2 == 2) - (a2 == 0), dc2 = (a2 == 1) - (a2 == 3);
@@ -129,7 +136,7 @@ __device__ __forceinline__ bool env_tick(int8_t* g, const StepParams& p, EnvStat
                     int& rr = i ? r2 : r1; int& cc = i ? c2 : c1;
                     const int dr = i ? dr2 : dr1, dc = i ? dc2 : dc1;
                     if (i) { rr += dr; cc += dc; }
-                    if (rr >= 0 && cc >= 0 && rr < p.W && cc < p.H && g[(rr + 1) * Hc + cc + 1] == TRON_TILE_EMPTY) {
+                    if (rr >= 0 && cc >= 0 && rr < p.W && cc < p.H && g.get(rr, cc) == TRON_TILE_EMPTY) {
                         bool slip;
                         const long long mant = (long long)((i ? sr.y : sr.x) >> 8);
                         if (p.slide_mode == TRON_SLIDE_TAPE) slip = p.slide_tape[2 * tn + i] != 0;
@@ -139,7 +146,7 @@ __device__ __forceinline__ bool env_tick(int8_t* g, const StepParams& p, EnvStat
                             slip = mant * 1000 <= K * 16777216;
                         }
                         if (slip) {
-                            g[(rr + 1) * Hc + cc + 1] = i ? TRON_TILE_P2_SLIDE : TRON_TILE_P1_SLIDE;
+                            g.put(rr, cc, i ? TRON_TILE_P2_SLIDE : TRON_TILE_P1_SLIDE);
                             rr += dr; cc += dc;
                         }
                     }
@@ -149,20 +156,19 @@ __device__ __forceinline__ bool env_tick(int8_t* g, const StepParams& p, EnvStat
             }
             // reference game.py:205-214: P1 fully resolved before P2, head written in every case
             bool al1 = e.flags & TRON_FLAG_ALIVE1, al2 = e.flags & TRON_FLAG_ALIVE2;
-            const int i1 = (r1 + 1) * Hc + c1 + 1;
-            const int i2 = (r2 + 1) * Hc + c2 + 1;
-            const int8_t t1 = g[i1];
-            const int8_t t2 = i2 == i1 ? (int8_t)TRON_TILE_P1_HEAD : g[i2];  // P2 sees P1's freshly written head
+            const bool same = r1 == r2 && c1 == c2;
+            const int t1 = g.get(r1, c1);
+            const int t2 = same ? (int)TRON_TILE_P1_HEAD : g.get(r2, c2);  // P2 sees P1's freshly written head
             if (r1 < 0 || c1 < 0 || r1 >= p.W || c1 >= p.H || t1 != TRON_TILE_EMPTY) al1 = false;
             if (r2 < 0 || c2 < 0 || r2 >= p.W || c2 >= p.H || t2 != TRON_TILE_EMPTY) al2 = false;
-            g[i1] = TRON_TILE_P1_HEAD;
-            g[i2] = TRON_TILE_P2_HEAD;  // written second: wins a shared cell
+            g.put(r1, c1, TRON_TILE_P1_HEAD);
+            g.put(r2, c2, TRON_TILE_P2_HEAD);  // written second: wins a shared cell
             if (TRACK) { box_add(bx, 0, r1, c1); box_add(bx, 1, r2, c2); }
             // reference game.py:264-277
             const int n_alive = (int)al1 + (int)al2;
             if (n_alive <= 1) {
                 done = 1;
-                if (n_alive == 1 && (r1 != r2 || c1 != c2)) winner = al1 ? 1u : 2u;
+                if (n_alive == 1 && !same) winner = al1 ? 1u : 2u;
             }
             e.flags = (al1 ? TRON_FLAG_ALIVE1 : 0u) | (al2 ? TRON_FLAG_ALIVE2 : 0u) | (done ? TRON_FLAG_DONE : 0u) |
                       (winner << TRON_FLAG_WINNER_SHIFT) | (TRACK ? (e.flags & TRON_FLAG_BOXES_VALID) : 0u);

@@ -54,8 +54,8 @@ class GpuEnvNumpy:
         return s
 
 
-def make_pair(n_envs, width=10, height=10, **kw):
-    return GpuEnvNumpy(n_envs, width, height, **kw), oc.OracleEnv(n_envs, width, height, **kw)
+def make_pair(n_envs, width=10, height=10, layout="tile8", **kw):
+    return GpuEnvNumpy(n_envs, width, height, layout=layout, **kw), oc.OracleEnv(n_envs, width, height, **kw)
 
 
 def assert_same_step(got, want, what=""):

@@ -1,0 +1,44 @@
+#!/usr/bin/env python
+"""BASELINE configs #3 / #4: batched DDQN self-play loop with the GPU replay ring.
+
+  python tools/train_ddqn.py --envs 65536 --ticks 40                                   # config #3 (1 GPU)
+  torchrun --nproc-per-node 8 tools/train_ddqn.py --envs 131072 --ticks 40            # config #4 (1M envs, NCCL grad all-reduce)
+Prints per-phase device time so "bottlenecked on the network, not the environment" can be read off directly.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import tron_b200  # noqa: E402
+from tron_b200 import dropin  # noqa: E402
+
+dropin.install()
+import DDQN  # noqa: E402
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--ticks", type=int, default=40)
+    ap.add_argument("--learn-every", type=int, default=4)
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    logs = []
+    agent, env = DDQN.train(n_envs=a.envs, env_steps=a.ticks, learn_every=a.learn_every, log=lambda t, d: logs.append(d))
+    warm = logs[len(logs) // 4:]
+    fw = sum(d["forward_ms"] for d in warm) / len(warm); er = sum(d["env_replay_ms"] for d in warm) / len(warm)
+    lr = sum(d["learn_ms"] for d in warm) / len(warm)
+    st = env.stats_dict()
+    if rank == 0:
+        print(json.dumps({"config": "DDQN self-play, %d envs/GPU x %d GPU(s), pop_up bf16 obs, GPU replay ring" % (a.envs, world),
+                          "ms_per_tick": {"q_forward(2N obs)": fw, "select+env_step+replay_push": er, "sample+learn(+allreduce)": lr},
+                          "env_fraction_of_tick": er / (fw + er + lr), "env_steps_per_s_per_gpu": a.envs / ((fw + er + lr) * 1e-3),
+                          "loss": logs[-1]["loss"], "episodes": st["episodes"], "mean_episode_ticks": st["ep_ticks"] / max(1, st["episodes"]),
+                          "replay_len": len(agent.memory)}))
+    if world > 1:
+        torch.distributed.destroy_process_group()

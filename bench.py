@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--width", type=int, default=10)
     ap.add_argument("--obs-dtype", default="bf16", choices=["bf16", "f32", "i8"])
     ap.add_argument("--enc", default="lut1", choices=["lut1", "popup3", "popup3_const", "none"])
+    ap.add_argument("--layout", default="bits10", choices=["bits10", "tile8"], help="state layout: 32-byte bit planes (10x10 only) or int8 Tile.value grid")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -166,8 +167,8 @@ def run_reference(a):
 # ----------------------------------------------------------------------------------------------- ours
 def workload_config(a, n_envs):
     return {"workload": "BASELINE config #2 scaled: %dx%d grid, uniform random actions (pre-generated u8 tape in HBM), auto-reset, "
-                        "%s observations (%s), fused step+obs" % (a.width, a.width, a.obs_dtype, a.enc),
-            "envs_per_gpu": n_envs, "grid": [a.width, a.width], "obs_dtype": a.obs_dtype, "obs_enc": a.enc,
+                        "%s observations (%s), fused step+obs, state layout %s" % (a.width, a.width, a.obs_dtype, a.enc, a.layout),
+            "envs_per_gpu": n_envs, "grid": [a.width, a.width], "obs_dtype": a.obs_dtype, "obs_enc": a.enc, "state_layout": a.layout,
             "l2_policy": "inputs larger than L2 (state+obs per GPU >> 126 MB), no flush", "parallelism": "env-sharded, no collective"}
 
 
@@ -208,7 +209,9 @@ def run_ours(a):
 
     N, W = a.envs_per_gpu, a.width
     tdt = {"bf16": torch.bfloat16, "f32": torch.float32, "i8": torch.int8}[a.obs_dtype]
-    env = BatchedTron(N, W, W, device=dev, obs_dtype=tdt, obs_enc=a.enc, reward="ddqn", auto_reset=True, seed=0, env_id_base=rank * N)
+    if a.layout == "bits10" and W != 10:
+        a.layout = "tile8"
+    env = BatchedTron(N, W, W, device=dev, obs_dtype=tdt, obs_enc=a.enc, reward="ddqn", auto_reset=True, seed=0, env_id_base=rank * N, layout=a.layout)
     obs = env.reset()
     # synthetic random-policy action stream, resident in HBM before the timed region
     tape = [env.random_actions(1000 + i) for i in range(4)]
@@ -248,7 +251,8 @@ def run_ours(a):
     C, P = env.C, env.P
     b_o = {"bf16": 2, "f32": 4, "i8": 1}[a.obs_dtype]
     M = 48
-    bytes_per_env_step = C * 1 * (1 + f_reset) + 2 * P * C * b_o + M
+    grid_bytes = 32 if a.layout == "bits10" else C  # state bytes per game as stored (C * b_g)
+    bytes_per_env_step = grid_bytes * (1 + f_reset) + 2 * P * C * b_o + M
     launch_ms = ms / a.steps
     achieved = bytes_per_env_step * N / (launch_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -258,11 +262,11 @@ def run_ours(a):
         pass
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%s_%d" % (a.obs_dtype, a.enc, N))
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s_%s_%s_%d" % (a.layout, a.obs_dtype, a.enc, N))
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "step_tile_kernel", "bytes_per_env_step": bytes_per_env_step, "reset_fraction": f_reset,
+                "peak_source": peak_src, "kernel": "step_bits10_kernel" if a.layout == "bits10" else "step_tile_kernel", "state_bytes_per_game": grid_bytes, "bytes_per_env_step": bytes_per_env_step, "reset_fraction": f_reset,
                 "envs_per_launch": N, "launch_ms": launch_ms, "frac_of_8TBs_nominal": achieved / 8000.0}
 
     # e2e: the same workload through the host-buffer C-ABI front end (pinned host arrays in, host arrays out)
@@ -272,7 +276,7 @@ def run_ours(a):
         torch.cuda.empty_cache()
         h = HostTron(N, W, W, obs_dtype={"bf16": abi.BF16, "f32": abi.F32, "i8": abi.I8}[a.obs_dtype],
                      obs_enc={"lut1": abi.ENC_LUT1, "popup3": abi.ENC_POPUP3, "popup3_const": abi.ENC_POPUP3_CONST, "none": abi.ENC_NONE}[a.enc],
-                     reward="ddqn", seed=0, env_id_base=rank * N, n_chunks=16)
+                     reward="ddqn", seed=0, env_id_base=rank * N, n_chunks=16, layout=a.layout)
         h.reset()
         host_tape = [t.cpu().numpy() for t in tape]
         h.step(host_tape[0])
@@ -290,7 +294,7 @@ def run_ours(a):
     # launch-bound regime of the literal config #2 size: 4096 envs, T ticks per launch (tron_step_many)
     small = None
     if rank == 0:
-        env_s = BatchedTron(4096, W, W, device=dev, obs_dtype=tdt, obs_enc=a.enc, seed=0)
+        env_s = BatchedTron(4096, W, W, device=dev, obs_dtype=tdt, obs_enc=a.enc, seed=0, layout=a.layout)
         env_s.reset()
         env_s.step_many(64)
         torch.cuda.synchronize()

@@ -9,4 +9,5 @@ from sweep import run  # noqa: E402
 if __name__ == "__main__":
     n, w, dt, enc = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4]
     steps = int(sys.argv[5]) if len(sys.argv) > 5 else 4
-    run("profile", n, w, dt, enc, steps=steps, warmup=2)
+    layout = sys.argv[6] if len(sys.argv) > 6 else "tile8"
+    run("profile", n, w, dt, enc, steps=steps, warmup=2, layout=layout)

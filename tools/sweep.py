@@ -20,9 +20,9 @@ except Exception:
     pass
 
 
-def run(name, N, W, dtype, enc, steps=20, warmup=3, actions="tape", auto_reset=True):
+def run(name, N, W, dtype, enc, steps=20, warmup=3, actions="tape", auto_reset=True, layout="tile8"):
     tdt = {"bf16": torch.bfloat16, "f32": torch.float32, "i8": torch.int8}[dtype]
-    env = BatchedTron(N, W, W, obs_dtype=tdt, obs_enc=enc, seed=0)
+    env = BatchedTron(N, W, W, obs_dtype=tdt, obs_enc=enc, seed=0, layout=layout)
     obs = env.reset()
     tape = [env.random_actions(100 + i) for i in range(4)] if actions == "tape" else [None] * 4
     reward = torch.empty((N, 2), dtype=torch.float32, device="cuda"); done = torch.empty(N, dtype=torch.uint8, device="cuda")
@@ -42,11 +42,11 @@ def run(name, N, W, dtype, enc, steps=20, warmup=3, actions="tape", auto_reset=T
     C, P = env.C, env.P
     b_o = {"bf16": 2, "f32": 4, "i8": 1}[dtype]
     if P:
-        B = C * (1 + f) + 2 * P * C * b_o + 48
+        B = (32 if layout == "bits10" else C) * (1 + f) + 2 * P * C * b_o + 48
     else:
         B = 320 + f * C  # SURVEY 8d pure-step sector model
     rate = N / (ms * 1e-3)
-    out = dict(case=name, envs=N, grid=W, obs=dtype, enc=enc, ms_per_step=ms, env_steps_per_s=rate, reset_fraction=f, bytes_per_env_step=B,
+    out = dict(case=name, layout=layout, envs=N, grid=W, obs=dtype, enc=enc, ms_per_step=ms, env_steps_per_s=rate, reset_fraction=f, bytes_per_env_step=B,
                achieved_GBps=rate * B / 1e9, frac_of_measured_peak=rate * B / 1e9 / PEAK)
     print(json.dumps(out), flush=True)
     del env, obs
@@ -57,7 +57,12 @@ def run(name, N, W, dtype, enc, steps=20, warmup=3, actions="tape", auto_reset=T
 def main():
     quick = "--quick" in sys.argv
     M = 1 << 20
-    run("10x10 bf16 1-plane (headline)", 4 * M, 10, "bf16", "lut1")
+    for lay in ("bits10", "tile8"):
+        run("10x10 bf16 1-plane (headline)", 4 * M, 10, "bf16", "lut1", layout=lay)
+    run("10x10 f32 1-plane", 2 * M, 10, "f32", "lut1", layout="bits10")
+    run("10x10 i8 1-plane", 4 * M, 10, "i8", "lut1", layout="bits10")
+    run("10x10 bf16 pop_up 3-plane (DDQN path)", 2 * M, 10, "bf16", "popup3", layout="bits10")
+    run("10x10 pure step (no obs)", 8 * M, 10, "bf16", "none", layout="bits10")
     run("10x10 bf16 1-plane, in-kernel Philox policy", 4 * M, 10, "bf16", "lut1", actions="rng")
     run("10x10 f32 1-plane", 2 * M, 10, "f32", "lut1")
     run("10x10 i8 1-plane", 4 * M, 10, "i8", "lut1")

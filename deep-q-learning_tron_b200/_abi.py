@@ -20,6 +20,7 @@ LAYOUT_TILE8 = 0
 LAYOUT_BITS10 = 1
 OPT_SPARSE_MIN_CELLS = 1
 SLIDE_NONE, SLIDE_TAPE, SLIDE_ICE, SLIDE_TEMPER = 0, 1, 2, 3
+SPAWN_UNIFORM, SPAWN_FAIR = 0, 1
 STATS_SLOTS, STATS_FIELDS = 64, 8
 (STAT_EPISODES, STAT_P1_WINS, STAT_P2_WINS, STAT_DRAWS, STAT_EP_TICKS, STAT_BAD_ACTION,
  STAT_ENV_STEPS) = range(7)
@@ -53,7 +54,7 @@ class StepArgs(C.Structure):
         ("lut", C.c_int8 * 6), ("pad0", C.c_int8 * 2), ("const_plane", C.c_float),
         ("reward", C.c_void_p), ("reward_table", Reward),
         ("done", C.c_void_p), ("winner", C.c_void_p), ("ep_len_out", C.c_void_p),
-        ("auto_reset", C.c_int32), ("spawn", C.c_void_p),
+        ("auto_reset", C.c_int32), ("spawn", C.c_void_p), ("spawn_mode", C.c_int32),
         ("seed", C.c_uint64), ("counter", C.c_uint64), ("env_id_base", C.c_uint64),
         ("slide_mode", C.c_int32), ("slide_rate", C.c_float), ("slide_tape", C.c_void_p),
         ("slide_params", C.c_void_p),

@@ -29,7 +29,7 @@ _SIGS = {
     "tron_enc_planes": (C.c_int, [_i]),
     "tron_dtype_size": (C.c_int, [_i]),
     "tron_build_plane_tables": (C.c_int, [_vp, _i, _vp]),
-    "tron_reset": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _vp, _u64, _u64, _u64, _vp]),
+    "tron_reset": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _u64, _u64, _u64, _vp]),
     "tron_step": (C.c_int, [C.POINTER(abi.StepArgs), _vp]),
     "tron_observe": (C.c_int, [C.POINTER(abi.StepArgs), _vp]),
     "tron_step_many": (C.c_int, [C.POINTER(abi.StepArgs), _vp]),

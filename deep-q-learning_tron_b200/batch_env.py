@@ -43,10 +43,11 @@ class BatchedTron:
 
     def __init__(self, n_envs, width=10, height=10, device="cuda", obs_dtype=torch.bfloat16, obs_enc="lut1", lut=None,
                  const_plane=0.0, reward="ddqn", auto_reset=True, seed=0, env_id_base=0, slide_mode=None,
-                 slide_rate=0.15, collect_stats=True, layout="tile8"):
+                 slide_rate=0.15, collect_stats=True, layout="tile8", spawn_mode="uniform"):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.layout = _LAYOUT_OF[layout] if isinstance(layout, str) else int(layout)
+        self.spawn_mode = {"uniform": abi.SPAWN_UNIFORM, "fair": abi.SPAWN_FAIR}[spawn_mode] if isinstance(spawn_mode, str) else int(spawn_mode)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.TronError("BatchedTron needs a CUDA device; there is no CPU fallback")
@@ -85,7 +86,7 @@ class BatchedTron:
         a = abi.new_step_args(n_envs=self.N, width=self.W, height=self.H, layout=self.layout, state=self.state.data_ptr(),
                               obs_dtype=self.obs_dtype, obs_enc=self.obs_enc, lut=self.lut, const_plane=self.const_plane,
                               reward_table=self.reward_table, auto_reset=int(self.auto_reset), seed=self.seed,
-                              env_id_base=self.env_id_base, slide_mode=self.slide_mode, slide_rate=self.slide_rate,
+                              env_id_base=self.env_id_base, slide_mode=self.slide_mode, slide_rate=self.slide_rate, spawn_mode=self.spawn_mode,
                               slide_params=_ptr(self.slide_params), stats=_ptr(self.stats))
         for k, v in kw.items():
             setattr(a, k, v)
@@ -107,7 +108,7 @@ class BatchedTron:
         sp = self._dev(spawn, torch.int8)
         mk = self._dev(mask, torch.uint8)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tron_reset(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(sp), _ptr(mk),
+            _lib.check(self.lib.tron_reset(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(sp), self.spawn_mode, _ptr(mk),
                                            self.seed, counter, self.env_id_base, self._stream()), "tron_reset")
         return self.observe(obs) if self.P else None
 

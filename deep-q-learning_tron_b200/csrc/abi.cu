@@ -80,11 +80,12 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
         p.reward = a->reward; p.done = a->done; p.winner = a->winner; p.eplen = a->ep_len_out;
         p.spawn = a->spawn; p.slide_tape = a->slide_tape; p.slide_params = a->slide_params; p.stats = (unsigned long long*)a->stats;
         p.auto_reset = a->auto_reset; p.slide_mode = a->slide_mode;
+        if (a->spawn_mode != TRON_SPAWN_UNIFORM && a->spawn_mode != TRON_SPAWN_FAIR) return TRON_ERR_INVALID;
         p.ice_thr = (long long)((double)a->slide_rate * 16777216.0);
         p.r_base = a->reward_table.step_base; p.r_tick = a->reward_table.step_per_tick;
         p.r_win = a->reward_table.win; p.r_lose = a->reward_table.lose; p.r_draw = a->reward_table.draw;
     }
-    p.seed = a->seed; p.counter = a->counter; p.env_base = a->env_id_base;
+    p.seed = a->seed; p.counter = a->counter; p.env_base = a->env_id_base; p.spawn_mode = a->spawn_mode;
     return TRON_OK;
 }
 
@@ -175,12 +176,13 @@ int tron_build_plane_tables(const int8_t lut6_in[6], int obs_enc, int8_t* tab) {
     return LP;
 }
 
-int tron_reset(void* state, int n_envs, int width, int height, int layout, const int8_t* spawn, const uint8_t* env_mask,
+int tron_reset(void* state, int n_envs, int width, int height, int layout, const int8_t* spawn, int spawn_mode, const uint8_t* env_mask,
                uint64_t seed, uint64_t counter, uint64_t env_id_base, tron_stream_t stream) {
+    if (spawn_mode != TRON_SPAWN_UNIFORM && spawn_mode != TRON_SPAWN_FAIR) return TRON_ERR_INVALID;
     tron_step_args a;
     memset(&a, 0, sizeof a);
     a.struct_size = sizeof a; a.n_envs = n_envs; a.width = width; a.height = height; a.layout = layout; a.state = state;
-    a.seed = seed; a.counter = counter; a.env_id_base = env_id_base;
+    a.seed = seed; a.counter = counter; a.env_id_base = env_id_base; a.spawn_mode = spawn_mode;
     StepParams p;
     const int rc = fill_params(&a, MODE_RESET, p);
     if (rc != TRON_OK) return rc;

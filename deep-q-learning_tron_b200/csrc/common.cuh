@@ -12,7 +12,7 @@ namespace tron {
 // Philox4x32-10 counter-based RNG.  Counter = {tick counter (64b), stream id (48b) | tag | sub},
 // key = seed.  One stream per global env id, so results do not depend on how envs are sharded.
 // ---------------------------------------------------------------------------------------------
-enum : uint32_t { TAG_ACTION = 1, TAG_SPAWN = 2, TAG_SLIDE = 3, TAG_EPS = 4, TAG_SAMPLE = 5, TAG_TEMPER = 6 };
+enum : uint32_t { TAG_ACTION = 1, TAG_SPAWN = 2, TAG_SLIDE = 3, TAG_EPS = 4, TAG_SAMPLE = 5, TAG_TEMPER = 6, TAG_FAIR = 7 };
 
 __device__ __forceinline__ uint4 philox(unsigned long long seed, unsigned long long counter,
                                         unsigned long long stream, uint32_t tag, uint32_t sub) {
@@ -29,17 +29,26 @@ __device__ __forceinline__ uint4 philox(unsigned long long seed, unsigned long l
     return make_uint4(c0, c1, c2, c3);
 }
 
-// make_game spawn rule (reference tron/util.py:70-78): 4 uniform draws, re-draw only (x1,y1) while equal.
-__device__ __forceinline__ char4 rng_spawn(unsigned long long seed, unsigned long long counter,
-                                           unsigned long long env, int W, int H) {
+// make_game spawn rule (reference tron/util.py:46-84).  Uniform: 4 draws over the grid.  Fair (mode="fair", util.py:48-62): a
+// random point, P1 uniform in the clipped 3x3 box around it, P2 uniform in the point-mirrored box.  Either way only
+// (x1,y1) is re-drawn while the two heads coincide (util.py:76-78).
+__device__ __forceinline__ char4 rng_spawn(unsigned long long seed, unsigned long long counter, unsigned long long env, int W, int H,
+                                           int fair) {
+    int lo1x = 0, hi1x = W - 1, lo1y = 0, hi1y = H - 1, lo2x = 0, hi2x = W - 1, lo2y = 0, hi2y = H - 1;
+    if (fair) {
+        const uint4 q = philox(seed, counter, env, TAG_FAIR, 0);
+        const int py = (int)__umulhi(q.x, (uint32_t)H), px = (int)__umulhi(q.y, (uint32_t)W);
+        lo1x = max(0, px - 1); hi1x = min(W - 1, px + 1); lo1y = max(0, py - 1); hi1y = min(H - 1, py + 1);
+        lo2x = W - 1 - hi1x; hi2x = W - 1 - lo1x; lo2y = H - 1 - hi1y; hi2y = H - 1 - lo1y;
+    }
     uint4 r = philox(seed, counter, env, TAG_SPAWN, 0);
-    int x1 = (int)__umulhi(r.x, (uint32_t)W), y1 = (int)__umulhi(r.y, (uint32_t)H);
-    const int x2 = (int)__umulhi(r.z, (uint32_t)W), y2 = (int)__umulhi(r.w, (uint32_t)H);
+    int x1 = lo1x + (int)__umulhi(r.x, (uint32_t)(hi1x - lo1x + 1)), y1 = lo1y + (int)__umulhi(r.y, (uint32_t)(hi1y - lo1y + 1));
+    const int x2 = lo2x + (int)__umulhi(r.z, (uint32_t)(hi2x - lo2x + 1)), y2 = lo2y + (int)__umulhi(r.w, (uint32_t)(hi2y - lo2y + 1));
     uint32_t attempt = 0;
     while (x1 == x2 && y1 == y2) {
-        if (++attempt >= 64) { x1 = (x2 + 1) % W; break; }
+        if (++attempt >= 64) { x1 = x1 == lo1x ? hi1x : lo1x; if (x1 == x2 && y1 == y2) y1 = y1 == lo1y ? hi1y : lo1y; break; }
         r = philox(seed, counter, env, TAG_SPAWN, attempt);
-        x1 = (int)__umulhi(r.x, (uint32_t)W); y1 = (int)__umulhi(r.y, (uint32_t)H);
+        x1 = lo1x + (int)__umulhi(r.x, (uint32_t)(hi1x - lo1x + 1)); y1 = lo1y + (int)__umulhi(r.y, (uint32_t)(hi1y - lo1y + 1));
     }
     return make_char4((signed char)x1, (signed char)y1, (signed char)x2, (signed char)y2);
 }

@@ -30,7 +30,7 @@ struct StepParams {
     unsigned long long seed, counter, env_base;
     long long ice_thr;
     int N, W, H, Hc, C, G, layout;
-    int T, obs_every_tick, auto_reset, slide_mode, action_dtype;
+    int T, obs_every_tick, auto_reset, slide_mode, action_dtype, spawn_mode;
     int P;  // planes written per player (lut planes + optional const plane)
     float r_base, r_tick, r_win, r_lose, r_draw, const_plane;
     PlaneTab tab[2][3];
@@ -207,7 +207,7 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
         }
     }
     if (do_reset) {  // fresh game (reference game.py:70-91, util.py:70-78); the caller rebuilds the cells
-        const char4 sp = p.spawn ? ((const char4*)p.spawn)[tn] : rng_spawn(p.seed, ctr, genv, p.W, p.H);
+        const char4 sp = p.spawn ? ((const char4*)p.spawn)[tn] : rng_spawn(p.seed, ctr, genv, p.W, p.H, p.spawn_mode);
         e.r1 = sp.x; e.c1 = sp.y; e.r2 = sp.z; e.c2 = sp.w;
         e.flags = TRON_FLAG_ALIVE1 | TRON_FLAG_ALIVE2 | (TRACK ? (e.flags & TRON_FLAG_BOXES_VALID) : 0u);
         e.k = 0;

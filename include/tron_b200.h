@@ -82,6 +82,12 @@ enum {
                               100 interior cells = 32 bytes per game; walls implicit, heads in the meta.  4.5x less state traffic. */
 };
 
+/* RNG spawn rules of make_game (tron/util.py:46-84) */
+enum {
+    TRON_SPAWN_UNIFORM = 0, /* both heads uniform over the grid, (x1,y1) re-drawn while equal (util.py:64-78) */
+    TRON_SPAWN_FAIR = 1     /* P1 in the clipped 3x3 box around a random point, P2 in the point-mirrored box (util.py:48-62) */
+};
+
 /* slide ("ice"/"temper") modes, tron/game.py:163-178 */
 enum {
     TRON_SLIDE_NONE = 0,
@@ -151,6 +157,7 @@ typedef struct tron_step_args {
 
     int32_t auto_reset;   /* 1: a finished game is replaced by a fresh one in the same call (ACKTR.py:296-310) */
     const int8_t* spawn;  /* device [N,4] = {x1,y1,x2,y2} used by envs that reset in this call; NULL -> RNG spawn (util.py:70-78) */
+    int32_t spawn_mode;   /* RNG spawn rule: TRON_SPAWN_UNIFORM (make_game default) | TRON_SPAWN_FAIR (make_game mode="fair", util.py:48-62) */
 
     uint64_t seed;        /* Philox key */
     uint64_t counter;     /* Philox counter low word: the caller advances it once per tick */
@@ -195,7 +202,7 @@ int tron_build_plane_tables(const int8_t lut6[6], int obs_enc, int8_t* tab /* [2
 /* Fresh games (Game.__init__, tron/game.py:70-91): grid border WALL, interior EMPTY, heads written.
  * spawn: device [N,4] {x1,y1,x2,y2} or NULL -> RNG spawn with make_game's re-draw rule (util.py:70-78).
  * env_mask: device [N] u8, only envs with mask != 0 are reset; NULL -> all. */
-int tron_reset(void* state, int n_envs, int width, int height, int layout, const int8_t* spawn,
+int tron_reset(void* state, int n_envs, int width, int height, int layout, const int8_t* spawn, int spawn_mode,
                const uint8_t* env_mask, uint64_t seed, uint64_t counter, uint64_t env_id_base,
                tron_stream_t stream);
 /* One tick of every env, fused with observation encoding, rewards, done/winner and auto-reset. */

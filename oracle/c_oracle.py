@@ -59,7 +59,7 @@ class OracleEnv:
 
     def __init__(self, n_envs, width=10, height=10, obs_dtype=abi.BF16, obs_enc=abi.ENC_LUT1, lut=None,
                  const_plane=0.0, reward="ddqn", auto_reset=True, seed=0, env_id_base=0,
-                 slide_mode=abi.SLIDE_NONE, slide_rate=0.0):
+                 slide_mode=abi.SLIDE_NONE, slide_rate=0.0, spawn_mode=0):
         self.N, self.W, self.H = n_envs, width, height
         self.C = abi.cells_per_env(width, height)
         self.P = abi.enc_planes(obs_enc)
@@ -69,6 +69,7 @@ class OracleEnv:
         self.reward_table = abi.Reward(*(abi.REWARD_POLICIES[reward] if isinstance(reward, str) else reward))
         self.auto_reset, self.seed, self.env_id_base = int(auto_reset), seed, env_id_base
         self.slide_mode, self.slide_rate = slide_mode, slide_rate
+        self.spawn_mode = spawn_mode
         self.state = np.zeros(lib().oracle_state_bytes(n_envs, width, height), np.uint8)
         self.slide_params = np.zeros((n_envs, 4), np.int8)
         self.stats = np.zeros(abi.STATS_FIELDS, np.uint64)
@@ -80,7 +81,7 @@ class OracleEnv:
                               obs_dtype=self.obs_dtype, obs_enc=self.obs_enc, lut=self.lut,
                               const_plane=self.const_plane, reward_table=self.reward_table,
                               auto_reset=self.auto_reset, seed=self.seed, env_id_base=self.env_id_base,
-                              slide_mode=self.slide_mode, slide_rate=self.slide_rate,
+                              slide_mode=self.slide_mode, slide_rate=self.slide_rate, spawn_mode=self.spawn_mode,
                               slide_params=_p(self.slide_params), stats=_p(self.stats))
         for k, v in kw.items():
             setattr(a, k, v)
@@ -98,7 +99,7 @@ class OracleEnv:
             self.counter += 1
         sp = None if spawn is None else np.ascontiguousarray(spawn, np.int8)
         mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
-        lib().oracle_reset(_p(self.state), self.N, self.W, self.H, _p(sp), _p(mk), C.c_uint64(self.seed),
+        lib().oracle_reset(_p(self.state), self.N, self.W, self.H, _p(sp), self.spawn_mode, _p(mk), C.c_uint64(self.seed),
                            C.c_uint64(counter), C.c_uint64(self.env_id_base))
         return self.observe() if self.P else None
 
@@ -241,3 +242,9 @@ def bench_random(n_envs, W, H, ticks, obs_dtype=abi.BF16, obs_enc=abi.ENC_LUT1, 
     sec = C.c_double()
     steps = lib().oracle_bench_random(n_envs, W, H, ticks, obs_dtype, obs_enc, C.c_uint64(seed), C.byref(sec))
     return steps, sec.value
+
+
+def fair_bounds(W, H, px, py):
+    b = (C.c_int * 8)()
+    lib().oracle_fair_bounds(W, H, px, py, b)
+    return list(b)

@@ -28,7 +28,7 @@
 #include "../include/tron_b200.h"
 
 /* ------------------------------------------------------------------ Philox4x32-10 (Salmon et al. 2011) */
-enum { TAG_ACTION = 1, TAG_SPAWN = 2, TAG_SLIDE = 3, TAG_EPS = 4, TAG_SAMPLE = 5, TAG_TEMPER = 6 };
+enum { TAG_ACTION = 1, TAG_SPAWN = 2, TAG_SLIDE = 3, TAG_EPS = 4, TAG_SAMPLE = 5, TAG_TEMPER = 6, TAG_FAIR = 7 };
 
 static void philox4x32_10(uint64_t seed, uint64_t counter, uint64_t stream, uint32_t tag, uint32_t sub,
                           uint32_t out[4]) {
@@ -59,17 +59,29 @@ static tron_meta* meta_of(void* state, int N, int W, int H) {
 }
 size_t oracle_state_bytes(int N, int W, int H) { return align256((size_t)N * cells_of(W, H)) + (size_t)N * 8u; }
 
-/* spawn rule of make_game (util.py:70-78): four uniform draws, re-draw only (x1,y1) while equal */
-static void rng_spawn(uint64_t seed, uint64_t counter, uint64_t env, int W, int H, int8_t s[4]) {
+/* box bounds of make_game(mode="fair") around point (px,py) (util.py:53-62): b = {lo1x,hi1x,lo1y,hi1y,lo2x,hi2x,lo2y,hi2y} */
+void oracle_fair_bounds(int W, int H, int px, int py, int b[8]) {
+    b[0] = px - 1 > 0 ? px - 1 : 0;          b[1] = px + 1 < W - 1 ? px + 1 : W - 1;
+    b[2] = py - 1 > 0 ? py - 1 : 0;          b[3] = py + 1 < H - 1 ? py + 1 : H - 1;
+    b[4] = W - 1 - b[1];                     b[5] = W - 1 - b[0];
+    b[6] = H - 1 - b[3];                     b[7] = H - 1 - b[2];
+}
+/* spawn rule of make_game (util.py:46-84): draws inside the boxes, re-draw only (x1,y1) while the heads coincide */
+static void rng_spawn(uint64_t seed, uint64_t counter, uint64_t env, int W, int H, int fair, int8_t s[4]) {
+    int b[8] = {0, W - 1, 0, H - 1, 0, W - 1, 0, H - 1};
     uint32_t r[4];
+    if (fair) {
+        philox4x32_10(seed, counter, env, TAG_FAIR, 0, r);
+        oracle_fair_bounds(W, H, (int)mulhi32(r[1], (uint32_t)W), (int)mulhi32(r[0], (uint32_t)H), b);
+    }
     philox4x32_10(seed, counter, env, TAG_SPAWN, 0, r);
-    int x1 = (int)mulhi32(r[0], (uint32_t)W), y1 = (int)mulhi32(r[1], (uint32_t)H);
-    int x2 = (int)mulhi32(r[2], (uint32_t)W), y2 = (int)mulhi32(r[3], (uint32_t)H);
+    int x1 = b[0] + (int)mulhi32(r[0], (uint32_t)(b[1] - b[0] + 1)), y1 = b[2] + (int)mulhi32(r[1], (uint32_t)(b[3] - b[2] + 1));
+    int x2 = b[4] + (int)mulhi32(r[2], (uint32_t)(b[5] - b[4] + 1)), y2 = b[6] + (int)mulhi32(r[3], (uint32_t)(b[7] - b[6] + 1));
     uint32_t attempt = 0;
     while (x1 == x2 && y1 == y2) {
-        if (++attempt >= 64) { x1 = (x2 + 1) % W; break; }
+        if (++attempt >= 64) { x1 = x1 == b[0] ? b[1] : b[0]; if (x1 == x2 && y1 == y2) y1 = y1 == b[2] ? b[3] : b[2]; break; }
         philox4x32_10(seed, counter, env, TAG_SPAWN, attempt, r);
-        x1 = (int)mulhi32(r[0], (uint32_t)W); y1 = (int)mulhi32(r[1], (uint32_t)H);
+        x1 = b[0] + (int)mulhi32(r[0], (uint32_t)(b[1] - b[0] + 1)); y1 = b[2] + (int)mulhi32(r[1], (uint32_t)(b[3] - b[2] + 1));
     }
     s[0] = (int8_t)x1; s[1] = (int8_t)y1; s[2] = (int8_t)x2; s[3] = (int8_t)y2;
 }
@@ -95,13 +107,13 @@ static void fresh_game(int8_t* g, tron_meta* m, int W, int H, const int8_t s[4])
     m->flags = TRON_FLAG_ALIVE1 | TRON_FLAG_ALIVE2; m->reserved = 0; m->ep_len = 0;
 }
 
-int oracle_reset(void* state, int N, int W, int H, const int8_t* spawn, const uint8_t* mask, uint64_t seed,
+int oracle_reset(void* state, int N, int W, int H, const int8_t* spawn, int spawn_mode, const uint8_t* mask, uint64_t seed,
                  uint64_t counter, uint64_t base) {
     int8_t* grid = grid_of(state); tron_meta* meta = meta_of(state, N, W, H); const int C = cells_of(W, H);
     for (int e = 0; e < N; ++e) {
         if (mask && !mask[e]) continue;
         int8_t s[4];
-        if (spawn) memcpy(s, spawn + 4 * (size_t)e, 4); else rng_spawn(seed, counter, base + (uint64_t)e, W, H, s);
+        if (spawn) memcpy(s, spawn + 4 * (size_t)e, 4); else rng_spawn(seed, counter, base + (uint64_t)e, W, H, spawn_mode, s);
         fresh_game(grid + (size_t)e * C, meta + e, W, H, s);
     }
     return 0;
@@ -253,7 +265,7 @@ static void step_tick(const tron_step_args* a, uint64_t counter, const void* act
                 st->f[winner == 0 ? TRON_STAT_DRAWS : winner == 1 ? TRON_STAT_P1_WINS : TRON_STAT_P2_WINS]++;
                 if (a->auto_reset) { /* ACKTR.py:296-310: replaced by a fresh game; returned obs is the new game's */
                     int8_t s[4];
-                    if (spawn) memcpy(s, spawn + 4 * (size_t)e, 4); else rng_spawn(a->seed, counter, env, W, H, s);
+                    if (spawn) memcpy(s, spawn + 4 * (size_t)e, 4); else rng_spawn(a->seed, counter, env, W, H, a->spawn_mode, s);
                     fresh_game(g, m, W, H, s);
                     if (a->slide_mode == TRON_SLIDE_TEMPER && a->slide_params) rng_temper(a->seed, counter, env, (int8_t*)a->slide_params + 4 * (size_t)e);
                 }
@@ -401,7 +413,7 @@ double oracle_bench_random(int n_envs, int W, int H, int ticks, int obs_dtype, i
     a.state = malloc(oracle_state_bytes(n_envs, W, H));
     a.obs = P ? malloc((size_t)n_envs * 2 * P * C * dsize(obs_dtype)) : NULL;
     a.reward = (float*)malloc((size_t)n_envs * 8); a.done = (uint8_t*)malloc((size_t)n_envs); a.winner = (uint8_t*)malloc((size_t)n_envs);
-    oracle_reset(a.state, n_envs, W, H, NULL, NULL, seed, 0, 0);
+    oracle_reset(a.state, n_envs, W, H, NULL, 0, NULL, seed, 0, 0);
     struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < ticks; ++t) { a.counter = (uint64_t)t + 1; oracle_step(&a); }
     clock_gettime(CLOCK_MONOTONIC, &t1);

@@ -255,6 +255,24 @@ def make_misc(G, U, P):
         gm = U.make_game(True, True)
         sp.append([int(gm.pps[0].position[0]), int(gm.pps[0].position[1]), int(gm.pps[1].position[0]), int(gm.pps[1].position[1])])
     out["make_game_spawns_seed123"] = sp
+    # make_game(mode="fair") box bounds (util.py:48-62): drive random.randint and record the (lo, hi) it is asked for
+    import tron.util as tu
+    fair = []
+    real_randint = tu.random.randint
+    try:
+        for py in range(10):
+            for px in range(10):
+                calls = []
+
+                def fake(a, b, _c=calls, _p=(py, px)):
+                    _c.append((a, b))
+                    return _p[len(_c) - 1] if len(_c) <= 2 else a + (len(_c) % 2) * (b - a)
+                tu.random.randint = fake
+                tu.make_game(True, True, mode="fair")
+                fair.append([px, py] + [v for ab in calls[2:6] for v in ab])  # x1, y1, x2, y2 ranges
+    finally:
+        tu.random.randint = real_randint
+    out["fair_bounds"] = fair
     # replay containers (plain python; importable even though Net() construction is broken)
     import DQN as RD
     import DDQN as RDD

@@ -252,7 +252,10 @@ def run_ours(a):
     b_o = {"bf16": 2, "f32": 4, "i8": 1}[a.obs_dtype]
     M = 48
     grid_bytes = 32 if a.layout == "bits10" else C  # state bytes per game as stored (C * b_g)
-    bytes_per_env_step = grid_bytes * (1 + f_reset) + 2 * P * C * b_o + M
+    if P:
+        bytes_per_env_step = grid_bytes * (1 + f_reset) + 2 * P * C * b_o + M
+    else:  # pure tick: <=4 sectors read+written, one metadata sector each way, reset amortisation
+        bytes_per_env_step = 320 + f_reset * grid_bytes
     launch_ms = ms / a.steps
     achieved = bytes_per_env_step * N / (launch_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -266,7 +269,7 @@ def run_ours(a):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "step_bits10_kernel" if a.layout == "bits10" else "step_tile_kernel", "state_bytes_per_game": grid_bytes, "bytes_per_env_step": bytes_per_env_step, "reset_fraction": f_reset,
+                "peak_source": peak_src, "kernel": "step_bits10_kernel" if a.layout == "bits10" else ("step_sparse_kernel" if (not P and C >= 1024) else "step_tile_kernel"), "state_bytes_per_game": grid_bytes, "bytes_per_env_step": bytes_per_env_step, "reset_fraction": f_reset,
                 "envs_per_launch": N, "launch_ms": launch_ms, "frac_of_8TBs_nominal": achieved / 8000.0}
 
     # e2e: the same workload through the host-buffer C-ABI front end (pinned host arrays in, host arrays out)

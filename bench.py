@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--enc", default="lut1", choices=["lut1", "popup3", "popup3_const", "none"])
     ap.add_argument("--layout", default="bits10", choices=["bits10", "tile8"], help="state layout: 32-byte bit planes (10x10 only) or int8 Tile.value grid")
     ap.add_argument("--e2e-steps", type=int, default=6)
+    ap.add_argument("--sustained-seconds", type=float, default=1.0, help="extra untimed-for-the-headline run of the same step (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -242,6 +243,26 @@ def run_ours(a):
     ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     st1 = env.stats_dict()
+    # sustained check (not the headline): the same step for >= 1 s, to show the K-step number is not a burst artefact
+    sustained = None
+    if a.sustained_seconds > 0:
+        n_sus = max(a.steps, int(a.sustained_seconds / (ms / a.steps * 1e-3)))
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+            time.sleep(0.1)
+        barrier(); torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw0 = time.perf_counter()
+        s0.record()
+        for i in range(n_sus):
+            one_step(i)
+        s1.record()
+        torch.cuda.synchronize(); barrier()
+        tw1 = time.perf_counter()
+        ms_sus = max_over_ranks(s0.elapsed_time(s1))
+        sustained = {"steps": n_sus, "seconds": ms_sus * 1e-3, "value": world * N * n_sus / (ms_sus * 1e-3), "unit": UNIT,
+                     "clocks": sampler2.stop(tw0, tw1) if rank == 0 else None}
     env_steps = st1["env_steps"] - st0["env_steps"]
     assert env_steps == N * a.steps, (env_steps, N * a.steps)
     f_reset = (st1["episodes"] - st0["episodes"]) / env_steps
@@ -293,6 +314,18 @@ def run_ours(a):
         e2e = {"value": sum_over_ranks(float(N * a.e2e_steps)) / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": 2 * N, "d2h_bytes_per_step": N * (frame + 8 + 2),
                "steps": a.e2e_steps, "api": "tron_host_env_step (pinned host buffers, 16 chunks over 4 streams)", "checksum": float(h.reward[:1024].sum())}
         h.close()
+        if a.obs_dtype != "i8" and P:  # same call with int8 observations (the reference returns integer arrays): 1/2 resp. 1/4 of the PCIe bytes
+            h8 = HostTron(N, W, W, obs_dtype=abi.I8, obs_enc={"lut1": abi.ENC_LUT1, "popup3": abi.ENC_POPUP3, "popup3_const": abi.ENC_POPUP3_CONST}[a.enc],
+                          reward="ddqn", seed=0, env_id_base=rank * N, n_chunks=16, layout=a.layout)
+            h8.reset(); h8.step(host_tape[0])
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(a.e2e_steps):
+                h8.step(host_tape[i & 3])
+            dt8 = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            e2e["int8_obs_variant"] = {"value": sum_over_ranks(float(N * a.e2e_steps)) / dt8, "unit": UNIT, "d2h_bytes_per_step": N * (2 * P * C + 10)}
+            h8.close()
 
     # launch-bound regime of the literal config #2 size: 4096 envs, T ticks per launch (tron_step_many)
     small = None
@@ -308,6 +341,16 @@ def run_ours(a):
         e1.record(); torch.cuda.synchronize()
         small = {"envs": 4096, "ticks_per_launch": 64, "value": 4096 * 64 * 10 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
                  "note": "literal BASELINE config #2 size: L2-resident and launch-bound, obs written every tick"}
+        from tron_b200.batch_env import GraphedStep
+        gs = GraphedStep(BatchedTron(4096, W, W, device=dev, obs_dtype=tdt, obs_enc=a.enc, seed=1, layout=a.layout), policy="random", ticks_per_replay=16)
+        gs.env.reset()
+        gs.replay(); torch.cuda.synchronize()
+        e0.record()
+        for _ in range(40):
+            gs.replay()
+        e1.record(); torch.cuda.synchronize()
+        small["cuda_graph_16_ticks_per_replay"] = {"value": 4096 * 16 * 40 / (e0.elapsed_time(e1) * 1e-3), "unit": UNIT,
+                                                   "note": "one tron_step launch per tick, 16 ticks captured in a CUDA graph, device-side RNG counter"}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -322,7 +365,7 @@ def run_ours(a):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic", "config": workload_config(a, N),
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": a.steps, "clocks": clocks, "small_n": small,
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": a.steps, "clocks": clocks, "sustained": sustained, "small_n": small,
                "episode_stats": {"reset_fraction": f_reset, "mean_episode_ticks": (st1["ep_ticks"] - st0["ep_ticks"]) / max(1, st1["episodes"] - st0["episodes"])}}
         print(json.dumps(out))
     if world > 1:

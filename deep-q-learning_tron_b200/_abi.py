@@ -55,7 +55,7 @@ class StepArgs(C.Structure):
         ("reward", C.c_void_p), ("reward_table", Reward),
         ("done", C.c_void_p), ("winner", C.c_void_p), ("ep_len_out", C.c_void_p),
         ("auto_reset", C.c_int32), ("spawn", C.c_void_p), ("spawn_mode", C.c_int32),
-        ("seed", C.c_uint64), ("counter", C.c_uint64), ("env_id_base", C.c_uint64),
+        ("seed", C.c_uint64), ("counter", C.c_uint64), ("env_id_base", C.c_uint64), ("counter_dev", C.c_void_p),
         ("slide_mode", C.c_int32), ("slide_rate", C.c_float), ("slide_tape", C.c_void_p),
         ("slide_params", C.c_void_p),
         ("stats", C.c_void_p),
@@ -112,7 +112,7 @@ EXPORTED_SYMBOLS = (
     "tron_state_bytes", "tron_state_offsets", "tron_cells_per_env", "tron_enc_planes",
     "tron_dtype_size", "tron_build_plane_tables", "tron_set_option",
     "tron_reset", "tron_step", "tron_observe", "tron_step_many", "tron_export_grid",
-    "tron_import_grid", "tron_random_actions", "tron_select_actions", "tron_pop_up",
+    "tron_import_grid", "tron_random_actions", "tron_select_actions", "tron_advance_counter", "tron_pop_up",
     "replay_push", "replay_gather", "replay_sample_indices",
     "tron_host_env_create", "tron_host_env_destroy", "tron_host_env_reset", "tron_host_env_step",
     "tron_host_env_state", "tron_host_alloc", "tron_host_free",

@@ -64,6 +64,7 @@ class BatchedTron:
         self.slide_mode = _SLIDE_OF[slide_mode] if (slide_mode is None or isinstance(slide_mode, str)) else int(slide_mode)
         self.slide_rate = float(slide_rate)
         self.counter = 0
+        self.counter_dev = None  # device u64; set by use_device_counter() so captured CUDA graphs advance the RNG between replays
         nbytes = C.c_size_t()
         _lib.check(self.lib.tron_state_bytes(self.N, self.W, self.H, self.layout, C.byref(nbytes)), "tron_state_bytes")
         with torch.cuda.device(self.device):
@@ -81,6 +82,27 @@ class BatchedTron:
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def use_device_counter(self):
+        """Keep the tick counter in device memory: every call then reads it on the GPU and bumps it with tron_advance_counter,
+        so a sequence of calls captured in a torch.cuda.CUDAGraph draws fresh random numbers on every replay."""
+        if self.counter_dev is None:
+            self.counter_dev = torch.full((1,), self.counter, dtype=torch.int64, device=self.device)
+            self.counter = 0
+        return self.counter_dev
+
+    def _take_counter(self, counter, n=1):
+        """-> (counter value for the call, device pointer or None, advance-after-call)"""
+        if counter is not None:
+            return counter, None, 0
+        if self.counter_dev is not None:
+            return 0, self.counter_dev.data_ptr(), n
+        c, self.counter = self.counter, self.counter + n
+        return c, None, 0
+
+    def _advance(self, n):
+        if n:
+            _lib.check(self.lib.tron_advance_counter(self.counter_dev.data_ptr(), n, self._stream()), "tron_advance_counter")
 
     def _args(self, **kw):
         a = abi.new_step_args(n_envs=self.N, width=self.W, height=self.H, layout=self.layout, state=self.state.data_ptr(),
@@ -104,7 +126,11 @@ class BatchedTron:
         """Fresh games (Game.__init__).  spawn: [N,4] int8 {x1,y1,x2,y2} or None (RNG, make_game rule).
         Returns the initial observation (or None for obs_enc='none')."""
         if counter is None:
-            counter, self.counter = self.counter, self.counter + 1
+            if self.counter_dev is not None:
+                counter = int(self.counter_dev.item())
+                self.counter_dev += 1
+            else:
+                counter, self.counter = self.counter, self.counter + 1
         sp = self._dev(spawn, torch.int8)
         mk = self._dev(mask, torch.uint8)
         with torch.cuda.device(self.device):
@@ -124,8 +150,7 @@ class BatchedTron:
              counter=None, want_ep_len=True):
         """One tick of every game.  actions: [N,2] uint8/int32/int64 tensor (P1,P2) or None (uniform random policy).
         Output tensors may be passed in to avoid allocation.  -> StepResult(obs, reward, done, winner, ep_len)"""
-        if counter is None:
-            counter, self.counter = self.counter, self.counter + 1
+        counter, cdev, adv = self._take_counter(counter)
         N, dev = self.N, self.device
         if actions is not None:
             if not torch.is_tensor(actions):
@@ -146,15 +171,15 @@ class BatchedTron:
             ep_len = torch.empty(N, dtype=torch.int32, device=dev)
         a = self._args(actions=_ptr(actions), action_dtype=0 if actions is None else _CODE_OF[actions.dtype], obs=_ptr(obs),
                        reward=reward.data_ptr(), done=done.data_ptr(), winner=winner.data_ptr(), ep_len_out=_ptr(ep_len),
-                       spawn=_ptr(sp), slide_tape=_ptr(sl), counter=counter)
+                       spawn=_ptr(sp), slide_tape=_ptr(sl), counter=counter, counter_dev=cdev)
         with torch.cuda.device(dev):
             _lib.check(self.lib.tron_step(C.byref(a), self._stream()), "tron_step")
+            self._advance(adv)
         return StepResult((obs, reward, done, winner, ep_len))
 
     def step_many(self, n_ticks, actions=None, spawn=None, obs_every_tick=True, counter=None):
         """n_ticks ticks in one launch.  actions [T,N,2] or None (RNG), spawn [T,N,4] or None (RNG)."""
-        if counter is None:
-            counter, self.counter = self.counter, self.counter + n_ticks
+        counter, cdev, adv = self._take_counter(counter, int(n_ticks))
         T, N, dev = int(n_ticks), self.N, self.device
         act = None
         if actions is not None:
@@ -169,9 +194,10 @@ class BatchedTron:
         ep_len = torch.empty((T, N), dtype=torch.int32, device=dev)
         a = self._args(actions=_ptr(act), action_dtype=0 if act is None else _CODE_OF[act.dtype], obs=_ptr(obs),
                        reward=reward.data_ptr(), done=done.data_ptr(), winner=winner.data_ptr(), ep_len_out=ep_len.data_ptr(),
-                       spawn=_ptr(sp), counter=counter, n_ticks=T, obs_every_tick=int(obs_every_tick))
+                       spawn=_ptr(sp), counter=counter, counter_dev=cdev, n_ticks=T, obs_every_tick=int(obs_every_tick))
         with torch.cuda.device(dev):
             _lib.check(self.lib.tron_step_many(C.byref(a), self._stream()), "tron_step_many")
+            self._advance(adv)
         return StepResult((obs, reward, done, winner, ep_len))
 
     def export(self):
@@ -194,22 +220,30 @@ class BatchedTron:
             _lib.check(self.lib.tron_import_grid(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(t), _ptr(h),
                                                  _ptr(al), _ptr(d), _ptr(w), _ptr(k), self._stream()), "tron_import_grid")
 
-    def random_actions(self, counter, out=None):
+    def random_actions(self, counter=None, out=None):
+        """counter=None with use_device_counter(): the draw of the *next* step() (same counter, not advanced)."""
         if out is None:
             out = torch.empty((self.N, 2), dtype=torch.uint8, device=self.device)
+        cdev = None
+        if counter is None:
+            counter, cdev = (0, self.counter_dev.data_ptr()) if self.counter_dev is not None else (self.counter, None)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tron_random_actions(out.data_ptr(), self.N, self.seed, counter, self.env_id_base, self._stream()),
+            _lib.check(self.lib.tron_random_actions(out.data_ptr(), self.N, self.seed, counter, cdev, self.env_id_base, self._stream()),
                        "tron_random_actions")
         return out
 
-    def select_actions(self, q, epsilon, counter, out=None):
-        """epsilon-greedy over q [N,2,4] or [2N,4] (float32/bfloat16) -> uint8 [N,2] (DDQN.py:90-110)."""
+    def select_actions(self, q, epsilon, counter=None, out=None):
+        """epsilon-greedy over q [N,2,4] or [2N,4] (float32/bfloat16) -> uint8 [N,2] (DDQN.py:90-110).
+        counter=None: the counter of the next step() (host value, or the device counter after use_device_counter())."""
         q2 = q.reshape(-1, 4).contiguous()
         if out is None:
             out = torch.empty(q2.shape[0], dtype=torch.uint8, device=self.device)
+        cdev = None
+        if counter is None:
+            counter, cdev = (0, self.counter_dev.data_ptr()) if self.counter_dev is not None else (self.counter, None)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.tron_select_actions(q2.data_ptr(), _CODE_OF[q2.dtype], q2.shape[0], float(epsilon), out.data_ptr(),
-                                                    self.seed, counter, 2 * self.env_id_base, self._stream()), "tron_select_actions")
+                                                    self.seed, counter, cdev, 2 * self.env_id_base, self._stream()), "tron_select_actions")
         return out.view(-1, 2) if out.numel() == 2 * self.N else out
 
     def stats_dict(self):
@@ -288,3 +322,42 @@ class HostTron:
             self.close()
         except Exception:
             pass
+
+
+class GraphedStep:
+    """One env tick captured as a CUDA graph (static buffers), for batch sizes where launch + Python overhead dominate.
+
+        gs = GraphedStep(env, policy="random")      # or policy="external": fill gs.actions before each replay
+        for _ in range(T): gs.replay()               # gs.obs / gs.reward / gs.done / gs.winner hold the latest tick
+
+    The RNG counter lives on the device (BatchedTron.use_device_counter), so every replay draws fresh actions / spawns.
+    `ticks_per_replay` > 1 captures that many consecutive ticks in one graph.
+    """
+
+    def __init__(self, env, policy="random", ticks_per_replay=1):
+        self.env = env
+        env.use_device_counter()
+        N, dev = env.N, env.device
+        self.actions = torch.zeros((N, 2), dtype=torch.uint8, device=dev)
+        self.obs = env.new_obs() if env.P else None
+        self.reward = torch.empty((N, 2), dtype=torch.float32, device=dev)
+        self.done = torch.empty(N, dtype=torch.uint8, device=dev)
+        self.winner = torch.empty(N, dtype=torch.uint8, device=dev)
+        self.ticks = int(ticks_per_replay)
+
+        def body():
+            for _ in range(self.ticks):
+                act = None if policy == "random" else self.actions
+                env.step(act, obs=self.obs, reward=self.reward, done=self.done, winner=self.winner, want_ep_len=False)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside capture
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            body()
+
+    def replay(self):
+        self.graph.replay()

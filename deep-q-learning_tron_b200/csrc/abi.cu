@@ -86,6 +86,7 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
         p.r_win = a->reward_table.win; p.r_lose = a->reward_table.lose; p.r_draw = a->reward_table.draw;
     }
     p.seed = a->seed; p.counter = a->counter; p.env_base = a->env_id_base; p.spawn_mode = a->spawn_mode;
+    p.counter_dev = (const unsigned long long*)a->counter_dev;
     return TRON_OK;
 }
 
@@ -241,16 +242,21 @@ int tron_import_grid(void* state, int n_envs, int width, int height, int layout,
     return launch_import_meta((char*)state + mo, n_envs, heads, alive, done, winner, ep_len, s);
 }
 
-int tron_random_actions(uint8_t* actions, int n_envs, uint64_t seed, uint64_t counter, uint64_t env_id_base, tron_stream_t stream) {
+int tron_random_actions(uint8_t* actions, int n_envs, uint64_t seed, uint64_t counter, const uint64_t* counter_dev, uint64_t env_id_base,
+                        tron_stream_t stream) {
     if (!actions || n_envs <= 0) return TRON_ERR_INVALID;
-    return launch_random_actions(actions, n_envs, seed, counter, env_id_base, (cudaStream_t)stream);
+    return launch_random_actions(actions, n_envs, seed, counter, counter_dev, env_id_base, (cudaStream_t)stream);
+}
+int tron_advance_counter(uint64_t* counter_dev, uint64_t delta, tron_stream_t stream) {
+    if (!counter_dev) return TRON_ERR_INVALID;
+    return launch_advance_counter(counter_dev, delta, (cudaStream_t)stream);
 }
 
 int tron_select_actions(const void* q, int q_dtype, int n_rows, float epsilon, uint8_t* actions, uint64_t seed, uint64_t counter,
-                        uint64_t row_id_base, tron_stream_t stream) {
+                        const uint64_t* counter_dev, uint64_t row_id_base, tron_stream_t stream) {
     if (!q || !actions || n_rows <= 0) return TRON_ERR_INVALID;
     if (((uintptr_t)q & (q_dtype == TRON_F32 ? 15u : 7u)) != 0) return TRON_ERR_ALIGN;
-    return launch_select_actions(q, q_dtype, n_rows, epsilon, actions, seed, counter, row_id_base, (cudaStream_t)stream);
+    return launch_select_actions(q, q_dtype, n_rows, epsilon, actions, seed, counter, counter_dev, row_id_base, (cudaStream_t)stream);
 }
 
 int tron_pop_up(const void* obs, int obs_dtype, int64_t n_maps, int cells, void* planes, int out_dtype, tron_stream_t stream) {

@@ -53,10 +53,17 @@ int launch_import_meta(void* meta, int n, const int8_t* heads, const uint8_t* al
 // ------------------------------------------------------------------------------------------------
 // policies
 // ------------------------------------------------------------------------------------------------
+__global__ void advance_counter_kernel(unsigned long long* c, unsigned long long delta) { *c += delta; }
+int launch_advance_counter(uint64_t* c, uint64_t delta, cudaStream_t s) {
+    advance_counter_kernel<<<1, 1, 0, s>>>((unsigned long long*)c, delta);
+    return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
+}
+
 __global__ void random_actions_kernel(uint8_t* actions, int n, unsigned long long seed, unsigned long long counter,
-                                      unsigned long long base) {
+                                      const unsigned long long* counter_dev, unsigned long long base) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
+    if (counter_dev) counter += *counter_dev;
     const uint4 r = philox(seed, counter, base + (unsigned long long)e, TAG_ACTION, 0);
     ((uchar2*)actions)[e] = make_uchar2((unsigned char)(r.x >> 30), (unsigned char)(r.y >> 30));
 }
@@ -64,9 +71,10 @@ __global__ void random_actions_kernel(uint8_t* actions, int n, unsigned long lon
 // epsilon-greedy (reference DDQN.py:90-110): explore iff u <= eps, else first argmax of the 4 q-values
 template <typename QT>
 __global__ void select_actions_kernel(const QT* __restrict__ q, int n, float eps, uint8_t* actions, unsigned long long seed,
-                                      unsigned long long counter, unsigned long long base) {
+                                      unsigned long long counter, const unsigned long long* counter_dev, unsigned long long base) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (counter_dev) counter += *counter_dev;
     float v[4];
     if constexpr (sizeof(QT) == 4) {
         const float4 f = ((const float4*)q)[i];
@@ -84,14 +92,15 @@ __global__ void select_actions_kernel(const QT* __restrict__ q, int n, float eps
     actions[i] = (uint8_t)(u <= eps ? (r.y >> 30) : (uint32_t)best);
 }
 
-int launch_random_actions(uint8_t* actions, int n, uint64_t seed, uint64_t counter, uint64_t base, cudaStream_t s) {
-    random_actions_kernel<<<(n + 255) / 256, 256, 0, s>>>(actions, n, seed, counter, base);
+int launch_random_actions(uint8_t* actions, int n, uint64_t seed, uint64_t counter, const uint64_t* cdev, uint64_t base, cudaStream_t s) {
+    random_actions_kernel<<<(n + 255) / 256, 256, 0, s>>>(actions, n, seed, counter, (const unsigned long long*)cdev, base);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 int launch_select_actions(const void* q, int q_dtype, int n, float eps, uint8_t* actions, uint64_t seed, uint64_t counter,
-                          uint64_t base, cudaStream_t s) {
-    if (q_dtype == TRON_F32) select_actions_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)q, n, eps, actions, seed, counter, base);
-    else if (q_dtype == TRON_BF16) select_actions_kernel<uint16_t><<<(n + 255) / 256, 256, 0, s>>>((const uint16_t*)q, n, eps, actions, seed, counter, base);
+                          const uint64_t* cdev, uint64_t base, cudaStream_t s) {
+    const unsigned long long* cd = (const unsigned long long*)cdev;
+    if (q_dtype == TRON_F32) select_actions_kernel<float><<<(n + 255) / 256, 256, 0, s>>>((const float*)q, n, eps, actions, seed, counter, cd, base);
+    else if (q_dtype == TRON_BF16) select_actions_kernel<uint16_t><<<(n + 255) / 256, 256, 0, s>>>((const uint16_t*)q, n, eps, actions, seed, counter, cd, base);
     else return TRON_ERR_INVALID;
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }

@@ -28,6 +28,7 @@ struct StepParams {
     const uint8_t* env_mask;  // MODE_RESET
     unsigned long long* stats;
     unsigned long long seed, counter, env_base;
+    const unsigned long long* counter_dev;
     long long ice_thr;
     int N, W, H, Hc, C, G, layout;
     int T, obs_every_tick, auto_reset, slide_mode, action_dtype, spawn_mode;
@@ -95,7 +96,7 @@ template <int MODE, bool TRACK, class Cells>
 __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState& e, long long env, int t, int tid, BoxRegs& bx) {
     bool do_reset = false;
     const unsigned long long genv = p.env_base + (unsigned long long)env;
-    const unsigned long long ctr = p.counter + (unsigned long long)t;
+    const unsigned long long ctr = p.counter + (p.counter_dev ? *p.counter_dev : 0ull) + (unsigned long long)t;
     const size_t tn = (size_t)t * (size_t)p.N + (size_t)env;
     if (MODE == MODE_RESET) {
         do_reset = p.env_mask ? p.env_mask[env] != 0 : true;

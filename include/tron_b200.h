@@ -162,6 +162,8 @@ typedef struct tron_step_args {
     uint64_t seed;        /* Philox key */
     uint64_t counter;     /* Philox counter low word: the caller advances it once per tick */
     uint64_t env_id_base; /* global id of env 0 of this shard (results independent of the sharding) */
+    const uint64_t* counter_dev; /* optional device u64 added to `counter` when the kernel runs: lets a captured CUDA graph
+                                    advance the RNG counter between replays (tron_advance_counter), NULL -> unused */
 
     int32_t slide_mode;   /* TRON_SLIDE_* */
     float slide_rate;     /* TRON_SLIDE_ICE */
@@ -223,12 +225,15 @@ int tron_import_grid(void* state, int n_envs, int width, int height, int layout,
 
 /* ---- policies ---- */
 /* Uniform random actions [n,2] u8 from Philox(seed; counter, env) -- same draws tron_step uses when actions==NULL. */
-int tron_random_actions(uint8_t* actions, int n_envs, uint64_t seed, uint64_t counter,
+int tron_random_actions(uint8_t* actions, int n_envs, uint64_t seed, uint64_t counter, const uint64_t* counter_dev,
                         uint64_t env_id_base, tron_stream_t stream);
 /* epsilon-greedy (DDQN.py:90-110): q device [n_rows,4] (TRON_F32|TRON_BF16); explore iff u <= epsilon.
  * Row i uses Philox stream row_id_base+i.  actions: device [n_rows] u8. */
 int tron_select_actions(const void* q, int q_dtype, int n_rows, float epsilon, uint8_t* actions,
-                        uint64_t seed, uint64_t counter, uint64_t row_id_base, tron_stream_t stream);
+                        uint64_t seed, uint64_t counter, const uint64_t* counter_dev, uint64_t row_id_base,
+                        tron_stream_t stream);
+/* *counter_dev += delta on the stream (one thread); put it after the calls that read counter_dev inside a CUDA graph. */
+int tron_advance_counter(uint64_t* counter_dev, uint64_t delta, tron_stream_t stream);
 
 /* pop_up on observations that are already encoded (reference tron/util.py:11-37): obs device [n_maps, cells]
  * (TRON_I8|TRON_I32|TRON_I64|TRON_BF16|TRON_F32) -> planes device [n_maps, 3, cells] = {wall, my, enemy}

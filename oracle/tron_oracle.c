@@ -292,7 +292,7 @@ int oracle_step_many(const tron_step_args* a) {
         const uint8_t* sl = a->slide_tape ? a->slide_tape + tt * N * 2 : NULL;
         void* obs = NULL;
         if (a->obs && P) obs = (a->obs_every_tick) ? (char*)a->obs + tt * N * 2 * P * C * dsize(a->obs_dtype) : (t == T - 1 ? a->obs : NULL);
-        step_tick(a, a->counter + (uint64_t)t, act, sp, sl, obs, a->reward ? a->reward + tt * N * 2 : NULL,
+        step_tick(a, a->counter + (a->counter_dev ? *a->counter_dev : 0) + (uint64_t)t, act, sp, sl, obs, a->reward ? a->reward + tt * N * 2 : NULL,
                   a->done ? a->done + tt * N : NULL, a->winner ? a->winner + tt * N : NULL,
                   a->ep_len_out ? a->ep_len_out + tt * N : NULL, &st);
     }

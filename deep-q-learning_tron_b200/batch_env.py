@@ -331,6 +331,7 @@ class GraphedStep:
         for _ in range(T): gs.replay()               # gs.obs / gs.reward / gs.done / gs.winner hold the latest tick
 
     The RNG counter lives on the device (BatchedTron.use_device_counter), so every replay draws fresh actions / spawns.
+    Construction plays `ticks_per_replay` real ticks once (warm-up before capture); capture itself executes nothing.
     `ticks_per_replay` > 1 captures that many consecutive ticks in one graph.
     """
 

@@ -219,6 +219,19 @@ __global__ void replay_gather_kernel(const replay_ring ring, const long long* __
         uint4* oa = (uint4*)((char*)out_s + (size_t)row * F * tron_elem(fd));
         uint4* ob = (uint4*)((char*)out_s2 + (size_t)row * F * tron_elem(fd));
         for (int v = threadIdx.x; v < nv; v += blockDim.x) { oa[v] = a[v]; ob[v] = b[v]; }
+    } else if (fd == TRON_BF16 && out_dtype == TRON_F32 && F % 8 == 0) {  // bf16 ring -> f32 batch: 16-byte loads, 2 x 16-byte stores
+        const int nv = F / 8;
+        const uint4* a = (const uint4*)((const uint16_t*)ring.state + (size_t)slot * F);
+        const uint4* b = (const uint4*)((const uint16_t*)ring.next_state + (size_t)slot * F);
+        uint4* oa = (uint4*)((float*)out_s + (size_t)row * F);
+        uint4* ob = (uint4*)((float*)out_s2 + (size_t)row * F);
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+            const uint4 x = a[v], y = b[v];
+            oa[2 * v] = make_uint4(x.x << 16, x.x & 0xFFFF0000u, x.y << 16, x.y & 0xFFFF0000u);
+            oa[2 * v + 1] = make_uint4(x.z << 16, x.z & 0xFFFF0000u, x.w << 16, x.w & 0xFFFF0000u);
+            ob[2 * v] = make_uint4(y.x << 16, y.x & 0xFFFF0000u, y.y << 16, y.y & 0xFFFF0000u);
+            ob[2 * v + 1] = make_uint4(y.z << 16, y.z & 0xFFFF0000u, y.w << 16, y.w & 0xFFFF0000u);
+        }
     } else {
         for (int j = threadIdx.x; j < F; j += blockDim.x) {
             store_out(out_s, out_dtype, row * F + j, load_f32(ring.state, fd, slot * F + j));

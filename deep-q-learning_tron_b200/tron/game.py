@@ -68,16 +68,21 @@ class Game:
         self.slide = _config.slide if slide_pram is None else slide_pram
         self._env = _gpu.new_env(width, height, slide_mode="tape" if mode in ("ice", "temper") else None)
         spawn = np.array([[pps[0].position[0], pps[0].position[1], pps[1].position[0], pps[1].position[1]]], np.int8)
-        obs = self._env.reset(spawn=spawn)
-        self.history = [HistoryElement(self._map_from_device(obs), None, None)]
+        self._finished = False
+        self.history = [HistoryElement(self._map_from_device(self._env.reset(spawn)), None, None)]
+
+    def __del__(self):
+        env = getattr(self, "_env", None)
+        if env is not None:
+            try:
+                env.release()  # the 1-env GPU context goes back to the pool for the next Game of this size
+            except Exception:
+                pass
 
     # ------------------------------------------------------------------ device <-> history
-    def _map_from_device(self, obs):
-        ex = self._env.export()
-        o = obs.cpu().numpy().astype(np.int64)
-        self._heads = ex["heads"].cpu().numpy()[0]
-        self._alive = ex["alive"].cpu().numpy()[0]
-        return Map._from_codes(self.width, self.height, ex["tiles"].cpu().numpy()[0], (o[0, 0, 0], o[0, 1, 0]))
+    def _map_from_device(self, snap):
+        self._heads, self._alive = snap["heads"], snap["alive"]
+        return Map._from_codes(self.width, self.height, snap["tiles"], (snap["obs1"], snap["obs2"]))
 
     def map(self):
         return self.history[-1].map.clone()
@@ -135,18 +140,18 @@ class Game:
             if not isinstance(pp.player, ACPlayer):
                 raise NotImplementedError("only ACPlayer-driven games are in scope (MinimaxPlayer / KeyboardPlayer are not)")
             pp.player.direction = pp.player.get_direction(actions[i])
-        if self._env.export()["done"].item():
+        if self._finished:
             return True  # finished game: frozen (documented deviation)
-        tape = self._slide_tape(actions) if self.mode in ("ice", "temper") else None
-        res = self._env.step(torch.tensor([actions], dtype=torch.uint8), slide_tape=tape)
+        tape = self._slide_tape(actions)[0] if self.mode in ("ice", "temper") else None
+        snap = self._env.step(actions, slide_tape=tape)
         self.history[-1].player_one_direction = self.pps[0].player.direction
         self.history[-1].player_two_direction = self.pps[1].player.direction
-        self.history.append(HistoryElement(self._map_from_device(res.obs), None, None))
+        self.history.append(HistoryElement(self._map_from_device(snap), None, None))
         for i, pp in enumerate(self.pps):
             pp.position = (int(self._heads[2 * i]), int(self._heads[2 * i + 1]))
             pp.alive = bool(self._alive[i])
-        self._last_done = bool(res.done.item())
-        self._last_winner = int(res.winner.item())
+        self._last_done = self._finished = bool(snap["done"])
+        self._last_winner = snap["winner"]
         self.next_p1 = self.history[-1].map.state_for_player(1)
         self.next_p2 = self.history[-1].map.state_for_player(2)
         if window:

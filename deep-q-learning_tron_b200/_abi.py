@@ -19,6 +19,7 @@ ENC_NONE, ENC_LUT1, ENC_POPUP3, ENC_POPUP3_CONST = 0, 1, 2, 3
 LAYOUT_TILE8 = 0
 LAYOUT_BITS10 = 1
 OPT_SPARSE_MIN_CELLS = 1
+OPT_TILE_BYTES = 2
 SLIDE_NONE, SLIDE_TAPE, SLIDE_ICE, SLIDE_TEMPER = 0, 1, 2, 3
 SPAWN_UNIFORM, SPAWN_FAIR = 0, 1
 STATS_SLOTS, STATS_FIELDS = 64, 8

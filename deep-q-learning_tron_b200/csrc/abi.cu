@@ -91,6 +91,9 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
 }
 
 long long g_sparse_min_cells = 1024;  // TRON_OPT_SPARSE_MIN_CELLS
+}  // namespace
+namespace tron { extern long long g_tile_bytes; }
+namespace {
 
 int dispatch(StepParams& p, int mode, int obs_dtype, int obs_enc, cudaStream_t s) {
     const int kind = enc_kind_of(obs_enc);
@@ -146,6 +149,7 @@ int tron_state_bytes(int n_envs, int width, int height, int layout, size_t* tota
 }
 int tron_set_option(int option, int64_t value) {
     if (option == TRON_OPT_SPARSE_MIN_CELLS && value >= 0) { g_sparse_min_cells = value; return TRON_OK; }
+    if (option == TRON_OPT_TILE_BYTES && value >= 1024 && value <= 200 * 1024) { tron::g_tile_bytes = value; return TRON_OK; }
     return TRON_ERR_INVALID;
 }
 

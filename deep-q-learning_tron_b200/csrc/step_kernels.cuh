@@ -70,8 +70,8 @@ __device__ __forceinline__ void encode_tile(const int8_t* tile, int nG, long lon
             char* obase = (char*)p.obs + tick_off;
             if constexpr (CH >= 4) {
                 const int per = C / CH;
-                for (int it = tid; it < nG * per; it += NT) {
-                    const int e = it / per, ch = it - e * per;
+                // one item = CH consecutive cells of one game -> one store per (player, plane)
+                auto emit = [&](int e, int ch) {
                     const int8_t* cells = tile + e * C + ch * CH;
                     uint32_t sel[CH / 4];
                     if constexpr (CH == 8) { const uint2 w = *(const uint2*)cells; sel[0] = cell_selector(w.x); sel[1] = cell_selector(w.y); }
@@ -94,6 +94,15 @@ __device__ __forceinline__ void encode_tile(const int8_t* tile, int nG, long lon
                             else if (NW == 2) st_cs((uint2*)dst, make_uint2(o[0], o[1 % NW]));
                             else *(uint32_t*)dst = o[0];
                         }
+                    }
+                };
+                if (C_T == 0 && per >= 4 * NT) {  // large grids: game-major loops, no per-item division
+                    for (int e = 0; e < nG; ++e)
+                        for (int ch = tid; ch < per; ch += NT) emit(e, ch);
+                } else {
+                    for (int it = tid; it < nG * per; it += NT) {
+                        const int e = it / per;
+                        emit(e, it - e * per);
                     }
                 }
             } else {  // scalar fallback for odd cell counts
@@ -188,14 +197,23 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
                 constexpr int V = (C_T != 0 && C_T % 16 == 0) ? 16 : 4;  // template copy granularity (C % 4 == 0 or scalar)
                 if ((C % V) == 0) {
                     const int per = C / V;
-                    for (int it = tid; it < nG * per; it += NT) {
-                        const int e = it / per, ch = it - e * per;
-                        if (!rflag[e]) continue;
+                    auto fill = [&](int e, int ch) {
                         if (V == 16) ((uint4*)(tile + e * C))[ch] = ((const uint4*)tmpl)[ch];
                         else ((uint32_t*)(tile + e * C))[ch] = ((const uint32_t*)tmpl)[ch];
                         const ushort2 h = hidx[e];
                         if ((int)h.x / V == ch) tile[e * C + h.x] = TRON_TILE_P1_HEAD;
                         if ((int)h.y / V == ch) tile[e * C + h.y] = TRON_TILE_P2_HEAD;
+                    };
+                    if (C_T == 0 && per >= 4 * NT) {
+                        for (int e = 0; e < nG; ++e) {
+                            if (!rflag[e]) continue;
+                            for (int ch = tid; ch < per; ch += NT) fill(e, ch);
+                        }
+                    } else {
+                        for (int it = tid; it < nG * per; it += NT) {
+                            const int e = it / per;
+                            if (rflag[e]) fill(e, it - e * per);
+                        }
                     }
                 } else {
                     for (int it = tid; it < nG * C; it += NT) {

@@ -192,7 +192,10 @@ int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* gr
                        size_t* boxes_off);
 /* Tuning knobs (process-wide).  TRON_OPT_SPARSE_MIN_CELLS: pure ticks (TRON_ENC_NONE) of games with at least this
  * many cells run thread-per-game on HBM with dirty-box resets instead of staging whole grids (default 1024). */
-enum { TRON_OPT_SPARSE_MIN_CELLS = 1 };
+enum {
+    TRON_OPT_SPARSE_MIN_CELLS = 1,
+    TRON_OPT_TILE_BYTES = 2 /* shared-memory budget of one tile of games in the generic-size fused kernel (default 18432) */
+};
 int tron_set_option(int option, int64_t value);
 int tron_cells_per_env(int width, int height);
 int tron_enc_planes(int obs_enc);

@@ -114,12 +114,24 @@ class BatchedTron:
             setattr(a, k, v)
         return a
 
-    def _dev(self, t, dtype):
+    def _dev(self, t, dtype, shape=None, name="tensor"):
+        """move/cast a user input to a contiguous device tensor and check its shape (the kernels trust sizes)"""
         if t is None:
             return None
         if not torch.is_tensor(t):
             t = torch.as_tensor(t)
-        return t.to(device=self.device, dtype=dtype).contiguous()
+        t = t.to(device=self.device, dtype=dtype).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError("%s must have shape %s, got %s" % (name, tuple(shape), tuple(t.shape)))
+        return t
+
+    def _out(self, t, shape, dtype, name):
+        """validate a caller-provided output buffer"""
+        if t is None:
+            return None
+        if (not torch.is_tensor(t) or t.device != self.device or t.dtype != dtype or tuple(t.shape) != tuple(shape) or not t.is_contiguous()):
+            raise ValueError("%s must be a contiguous %s tensor of shape %s on %s" % (name, dtype, tuple(shape), self.device))
+        return t
 
     # ------------------------------------------------------------------ API
     def reset(self, spawn=None, mask=None, obs=None, counter=None):
@@ -131,16 +143,19 @@ class BatchedTron:
                 self.counter_dev += 1
             else:
                 counter, self.counter = self.counter, self.counter + 1
-        sp = self._dev(spawn, torch.int8)
-        mk = self._dev(mask, torch.uint8)
+        sp = self._dev(spawn, torch.int8, (self.N, 4), "spawn")
+        mk = self._dev(mask, torch.uint8, (self.N,), "mask")
         with torch.cuda.device(self.device):
             _lib.check(self.lib.tron_reset(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(sp), self.spawn_mode, _ptr(mk),
                                            self.seed, counter, self.env_id_base, self._stream()), "tron_reset")
         return self.observe(obs) if self.P else None
 
     def observe(self, obs=None):
+        if not self.P:
+            raise ValueError("this environment was created with obs_enc='none'")
         if obs is None:
             obs = self.new_obs()
+        self._out(obs, (self.N, 2, self.P, self.W + 2, self.H + 2), _TORCH_OF[self.obs_dtype], "obs")
         a = self._args(obs=obs.data_ptr())
         with torch.cuda.device(self.device):
             _lib.check(self.lib.tron_observe(C.byref(a), self._stream()), "tron_observe")
@@ -157,8 +172,15 @@ class BatchedTron:
                 actions = torch.as_tensor(actions)
             if actions.device != dev or not actions.is_contiguous() or actions.dtype not in (torch.uint8, torch.int32, torch.int64):
                 actions = actions.to(device=dev, dtype=torch.uint8 if actions.dtype not in (torch.int32, torch.int64) else actions.dtype).contiguous()
-        sp = self._dev(spawn, torch.int8)
-        sl = self._dev(slide_tape, torch.uint8)
+            if tuple(actions.shape) != (N, 2):
+                raise ValueError("actions must have shape (%d, 2), got %s" % (N, tuple(actions.shape)))
+        sp = self._dev(spawn, torch.int8, (N, 4), "spawn")
+        sl = self._dev(slide_tape, torch.uint8, (N, 2), "slide_tape")
+        if self.slide_mode == abi.SLIDE_TAPE and sl is None:
+            raise ValueError("slide_mode='tape' needs a slide_tape for every step")
+        self._out(obs, (N, 2, self.P, self.W + 2, self.H + 2), _TORCH_OF.get(self.obs_dtype), "obs") if self.P else None
+        self._out(reward, (N, 2), torch.float32, "reward"); self._out(done, (N,), torch.uint8, "done")
+        self._out(winner, (N,), torch.uint8, "winner"); self._out(ep_len, (N,), torch.int32, "ep_len")
         if obs is None and self.P:
             obs = self.new_obs()
         if reward is None:
@@ -186,7 +208,11 @@ class BatchedTron:
             act = actions if torch.is_tensor(actions) else torch.as_tensor(actions)
             dt = act.dtype if act.dtype in (torch.int32, torch.int64) else torch.uint8
             act = act.to(device=dev, dtype=dt).contiguous()
-        sp = self._dev(spawn, torch.int8)
+            if tuple(act.shape) != (T, N, 2):
+                raise ValueError("actions must have shape (%d, %d, 2), got %s" % (T, N, tuple(act.shape)))
+        sp = self._dev(spawn, torch.int8, (T, N, 4), "spawn")
+        if self.slide_mode == abi.SLIDE_TAPE:
+            raise ValueError("step_many does not take a slide tape; use step() or slide_mode 'ice'/'temper'")
         obs = (self.new_obs(T) if obs_every_tick else self.new_obs()) if self.P else None
         reward = torch.empty((T, N, 2), dtype=torch.float32, device=dev)
         done = torch.empty((T, N), dtype=torch.uint8, device=dev)
@@ -214,8 +240,10 @@ class BatchedTron:
         return out
 
     def import_(self, tiles=None, heads=None, alive=None, done=None, winner=None, ep_len=None):
-        t = self._dev(tiles, torch.int8); h = self._dev(heads, torch.int8); al = self._dev(alive, torch.uint8)
-        d = self._dev(done, torch.uint8); w = self._dev(winner, torch.uint8); k = self._dev(ep_len, torch.int32)
+        N = self.N
+        t = self._dev(tiles, torch.int8, (N, self.W + 2, self.H + 2), "tiles"); h = self._dev(heads, torch.int8, (N, 4), "heads")
+        al = self._dev(alive, torch.uint8, (N, 2), "alive"); d = self._dev(done, torch.uint8, (N,), "done")
+        w = self._dev(winner, torch.uint8, (N,), "winner"); k = self._dev(ep_len, torch.int32, (N,), "ep_len")
         with torch.cuda.device(self.device):
             _lib.check(self.lib.tron_import_grid(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(t), _ptr(h),
                                                  _ptr(al), _ptr(d), _ptr(w), _ptr(k), self._stream()), "tron_import_grid")
@@ -235,9 +263,13 @@ class BatchedTron:
     def select_actions(self, q, epsilon, counter=None, out=None):
         """epsilon-greedy over q [N,2,4] or [2N,4] (float32/bfloat16) -> uint8 [N,2] (DDQN.py:90-110).
         counter=None: the counter of the next step() (host value, or the device counter after use_device_counter())."""
+        if q.device != self.device or q.dtype not in (torch.float32, torch.bfloat16) or q.numel() % 4:
+            raise ValueError("q must be a float32/bfloat16 tensor [..., 4] on %s" % self.device)
         q2 = q.reshape(-1, 4).contiguous()
         if out is None:
             out = torch.empty(q2.shape[0], dtype=torch.uint8, device=self.device)
+        elif out.numel() != q2.shape[0] or out.dtype != torch.uint8 or out.device != self.device or not out.is_contiguous():
+            raise ValueError("out must be a contiguous uint8 tensor with one element per q row")
         cdev = None
         if counter is None:
             counter, cdev = (0, self.counter_dev.data_ptr()) if self.counter_dev is not None else (self.counter, None)

@@ -209,7 +209,7 @@ __global__ void replay_gather_kernel(const replay_ring ring, const long long* __
                                      int out_dtype, long long* out_a, float* out_r, float* out_d) {
     const long long row = blockIdx.x;
     if (row >= k) return;
-    const long long slot = idx[row];
+    const long long slot = min(max(idx[row], 0ll), (long long)ring.capacity - 1);  // a bad index must not read outside the ring
     const int F = ring.frame_elems;
     const int fd = ring.frame_dtype;
     if (fd == out_dtype && ((size_t)F * tron_elem(fd)) % 16 == 0) {  // same dtype: 16-byte row copy

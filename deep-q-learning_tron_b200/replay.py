@@ -45,6 +45,10 @@ class ReplayRing:
         """Append n transitions.  state/next_state: [n, *frame_shape] (ring dtype), action uint8 [n], reward f32 [n],
         done uint8 [n] (done_stride=1) or [n/2] (done_stride=2: one flag per env, two players per env)."""
         n = action.numel()
+        if state.numel() != n * self.F or next_state.numel() != n * self.F or reward.numel() != n:
+            raise ValueError("push: state/next_state must hold %d frames of %d elements and reward %d values" % (n, self.F, n))
+        if done_stride not in (1, 2) or done.numel() * done_stride != n:
+            raise ValueError("push: done must hold n/done_stride flags (n=%d, done_stride=%d, got %d)" % (n, done_stride, done.numel()))
         tdt = _TORCH_OF[self.dt]
         state = state.to(device=self.device, dtype=tdt).contiguous()
         next_state = next_state.to(device=self.device, dtype=tdt).contiguous()
@@ -65,6 +69,8 @@ class ReplayRing:
     def sample_indices(self, k, counter=None):
         if counter is None:
             counter, self.sample_counter = self.sample_counter, self.sample_counter + 1
+        if not 0 < k <= min(len(self), 4096):
+            raise ValueError("sample_indices: need 0 < k <= min(len(ring)=%d, 4096), got %d" % (len(self), k))
         idx = torch.empty(k, dtype=torch.int64, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.replay_sample_indices(len(self), k, self.seed, counter, idx.data_ptr(), self._stream()),
@@ -75,6 +81,8 @@ class ReplayRing:
         """-> (states [k,*frame], actions i64 [k,1], rewards f32 [k,1], next_states, dones f32 [k,1])  (DDQN.py:191-200)"""
         idx = idx.to(device=self.device, dtype=torch.int64).contiguous()
         k = idx.numel()
+        if out_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("gather: out_dtype must be float32 or bfloat16")
         s = torch.empty((k,) + self.frame_shape, dtype=out_dtype, device=self.device)
         s2 = torch.empty_like(s)
         a = torch.empty((k, 1), dtype=torch.int64, device=self.device)

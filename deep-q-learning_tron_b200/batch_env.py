@@ -51,6 +51,8 @@ class BatchedTron:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.TronError("BatchedTron needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:  # "cuda" -> "cuda:<current>", so device comparisons with tensors are exact
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.N, self.W, self.H = int(n_envs), int(width), int(height)
         self.C = abi.cells_per_env(width, height)
         self.obs_enc = _ENC_OF[obs_enc] if isinstance(obs_enc, str) else int(obs_enc)

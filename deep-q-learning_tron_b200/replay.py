@@ -17,6 +17,8 @@ class ReplayRing:
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.capacity = int(capacity)
         self.frame_shape = tuple(frame_shape)
         self.F = 1

@@ -265,7 +265,7 @@ class BatchedTron:
     def select_actions(self, q, epsilon, counter=None, out=None):
         """epsilon-greedy over q [N,2,4] or [2N,4] (float32/bfloat16) -> uint8 [N,2] (DDQN.py:90-110).
         counter=None: the counter of the next step() (host value, or the device counter after use_device_counter())."""
-        if q.device != self.device or q.dtype not in (torch.float32, torch.bfloat16) or q.numel() % 4:
+        if q.device != self.device or q.dtype not in (torch.float32, torch.bfloat16) or q.dim() < 1 or q.shape[-1] != 4:
             raise ValueError("q must be a float32/bfloat16 tensor [..., 4] on %s" % self.device)
         q2 = q.reshape(-1, 4).contiguous()
         if out is None:

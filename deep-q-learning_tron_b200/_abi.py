@@ -113,7 +113,7 @@ EXPORTED_SYMBOLS = (
     "tron_state_bytes", "tron_state_offsets", "tron_cells_per_env", "tron_enc_planes",
     "tron_dtype_size", "tron_build_plane_tables", "tron_set_option",
     "tron_reset", "tron_step", "tron_observe", "tron_step_many", "tron_export_grid",
-    "tron_import_grid", "tron_random_actions", "tron_select_actions", "tron_advance_counter", "tron_pop_up",
+    "tron_import_grid", "tron_random_actions", "tron_select_actions", "tron_advance_counter", "tron_minimax_actions", "tron_pop_up",
     "replay_push", "replay_gather", "replay_sample_indices",
     "tron_host_env_create", "tron_host_env_destroy", "tron_host_env_reset", "tron_host_env_step",
     "tron_host_env_state", "tron_host_alloc", "tron_host_free",

@@ -280,6 +280,21 @@ class BatchedTron:
                                                     self.seed, counter, cdev, 2 * self.env_id_base, self._stream()), "tron_select_actions")
         return out.view(-1, 2) if out.numel() == 2 * self.N else out
 
+    def minimax_actions(self, player, tie_mode=1, counter=None, out=None, want_values=False):
+        """The move (0..3) the reference's MinimaxPlayer(2, voronoi) would make for `player` (1|2) in every game
+        (tron/minimax.py:296-310).  tie_mode 0 = first best move, 1 = uniform among the best (Philox)."""
+        tiles = self.state if self.layout == abi.LAYOUT_TILE8 else self.export()["tiles"]
+        if out is None:
+            out = torch.empty(self.N, dtype=torch.uint8, device=self.device)
+        vals = torch.empty((self.N, 4), dtype=torch.int32, device=self.device) if want_values else None
+        cdev = None
+        if counter is None:
+            counter, cdev = (0, self.counter_dev.data_ptr()) if self.counter_dev is not None else (self.counter, None)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tron_minimax_actions(tiles.data_ptr(), self.N, self.W, self.H, int(player), int(tie_mode), self.seed, counter, cdev,
+                                                     self.env_id_base, out.data_ptr(), _ptr(vals), self._stream()), "tron_minimax_actions")
+        return (out, vals) if want_values else out
+
     def stats_dict(self):
         """Summed on-device counters (episodes, wins, draws, ticks...).  Synchronises."""
         if self.stats is None:

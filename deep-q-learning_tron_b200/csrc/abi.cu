@@ -263,6 +263,13 @@ int tron_select_actions(const void* q, int q_dtype, int n_rows, float epsilon, u
     return launch_select_actions(q, q_dtype, n_rows, epsilon, actions, seed, counter, counter_dev, row_id_base, (cudaStream_t)stream);
 }
 
+int tron_minimax_actions(const int8_t* tiles, int n_envs, int width, int height, int player, int tie_mode, uint64_t seed, uint64_t counter,
+                         const uint64_t* counter_dev, uint64_t env_id_base, uint8_t* actions, int32_t* values, tron_stream_t stream) {
+    if (!tiles || !actions || !geometry_ok(n_envs, width, height) || (player != 1 && player != 2) || (tie_mode != 0 && tie_mode != 1)) return TRON_ERR_INVALID;
+    if ((width + 2) * (height + 2) > 256) return TRON_ERR_UNSUPPORTED;
+    return launch_minimax(tiles, n_envs, width, height, player, tie_mode, seed, counter, counter_dev, env_id_base, actions, values, (cudaStream_t)stream);
+}
+
 int tron_pop_up(const void* obs, int obs_dtype, int64_t n_maps, int cells, void* planes, int out_dtype, tron_stream_t stream) {
     if (!obs || !planes || n_maps <= 0 || cells <= 0) return TRON_ERR_INVALID;
     if (obs_dtype != TRON_F32 && obs_dtype != TRON_BF16 && obs_dtype != TRON_I8 && obs_dtype != TRON_I32 && obs_dtype != TRON_I64) return TRON_ERR_INVALID;

@@ -135,11 +135,16 @@ class Game:
 
     # ------------------------------------------------------------------ ticks
     def next_frame(self, action_p1, action_p2, window=None):
-        actions = [int(action_p1), int(action_p2)]
+        actions = [action_p1, action_p2]
         for i, pp in enumerate(self.pps):
-            if not isinstance(pp.player, ACPlayer):
-                raise NotImplementedError("only ACPlayer-driven games are in scope (MinimaxPlayer / KeyboardPlayer are not)")
-            pp.player.direction = pp.player.get_direction(actions[i])
+            if isinstance(pp.player, ACPlayer):
+                actions[i] = int(actions[i])
+                pp.player.direction = pp.player.get_direction(actions[i])
+            elif hasattr(pp.player, "action"):  # scripted player (MinimaxPlayer): it looks at the current map (game.py:182)
+                pp.player.direction = pp.player.action(self.map(), i + 1)
+                actions[i] = pp.player.direction.value - 1
+            else:
+                raise NotImplementedError("unsupported player type %r" % type(pp.player).__name__)
         if self._finished:
             return True  # finished game: frozen (documented deviation)
         tape = self._slide_tape(actions)[0] if self.mode in ("ice", "temper") else None

@@ -40,9 +40,9 @@ def make_game(p1, p2, mode=None, gamemode=None, slide_pram=None):
     while x1 == x2 and y1 == y2:
         x1 = random.randint(lo1x, hi1x)
         y1 = random.randint(lo1y, hi1y)
-    if not (p1 and p2):
-        raise NotImplementedError("MinimaxPlayer opponents are out of scope; pass p1=True, p2=True (ACPlayer)")
-    return Game(W, H, [PositionPlayer(1, ACPlayer(), [x1, y1]), PositionPlayer(2, ACPlayer(), [x2, y2])], gamemode, slide_pram)
+    from tron.minimax import MinimaxPlayer
+    return Game(W, H, [PositionPlayer(1, ACPlayer() if p1 else MinimaxPlayer(2, "voronoi"), [x1, y1]),
+                       PositionPlayer(2, ACPlayer() if p2 else MinimaxPlayer(2, "voronoi"), [x2, y2])], gamemode, slide_pram)
 
 
 def get_reward(game, constants):

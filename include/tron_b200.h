@@ -238,6 +238,14 @@ int tron_select_actions(const void* q, int q_dtype, int n_rows, float epsilon, u
 /* *counter_dev += delta on the stream (one thread); put it after the calls that read counter_dev inside a CUDA graph. */
 int tron_advance_counter(uint64_t* counter_dev, uint64_t delta, tron_stream_t stream);
 
+/* Scripted opponent: the action (0..3) MinimaxPlayer(2, voronoi) (tron/minimax.py:58-310) would take for `player` (1|2) in every
+ * game.  tiles: device [N, (W+2)(H+2)] Tile.value grids (the TRON_LAYOUT_TILE8 state itself, or tron_export_grid output);
+ * grids of at most 256 cells.  tie_mode 0: first best move / UP when boxed in; 1: Philox-uniform (random.choice / randint).
+ * values: optional device [N,4] int32 minimax value of each root move (INT32_MIN = move not expanded). */
+int tron_minimax_actions(const int8_t* tiles, int n_envs, int width, int height, int player, int tie_mode, uint64_t seed,
+                         uint64_t counter, const uint64_t* counter_dev, uint64_t env_id_base, uint8_t* actions,
+                         int32_t* values, tron_stream_t stream);
+
 /* pop_up on observations that are already encoded (reference tron/util.py:11-37): obs device [n_maps, cells]
  * (TRON_I8|TRON_I32|TRON_I64|TRON_BF16|TRON_F32) -> planes device [n_maps, 3, cells] = {wall, my, enemy}
  * (TRON_F32|TRON_BF16|TRON_I8).  The fused path (TRON_ENC_POPUP3) never materialises the 1-plane form. */

@@ -248,3 +248,13 @@ def fair_bounds(W, H, px, py):
     b = (C.c_int * 8)()
     lib().oracle_fair_bounds(W, H, px, py, b)
     return list(b)
+
+
+def minimax_actions(env, player, tie_mode=0, counter=0, want_values=False):
+    """MinimaxPlayer(2, voronoi) decisions for `player` in every game of an OracleEnv (tron/minimax.py)."""
+    act = np.zeros(env.N, np.uint8)
+    vals = np.zeros((env.N, 4), np.int32)
+    rc = lib().oracle_minimax_actions(_p(env.state), env.N, env.W, env.H, player, tie_mode, C.c_uint64(env.seed), C.c_uint64(counter),
+                                      C.c_uint64(env.env_id_base), _p(act), _p(vals))
+    assert rc == 0, rc
+    return (act, vals) if want_values else act

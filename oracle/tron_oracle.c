@@ -421,3 +421,131 @@ double oracle_bench_random(int n_envs, int W, int H, int ticks, int obs_dtype, i
     free(a.state); free(a.obs); free(a.reward); free(a.done); free(a.winner);
     return (double)n_envs * (double)ticks;
 }
+
+/* ------------------------------------------------------------------ scripted opponent: depth-2 minimax + Voronoi heuristic
+ * Restatement of MinimaxPlayer(2, voronoi).action (tron/minimax.py:58-310), quirks included:
+ *  - the search runs on the TRANSPOSED observation of the moving player (minimax.py:298): gm[i0][i1] = obs[i1][i0];
+ *  - heads are located with argmax / argmin over the flattened map (minimax.py:151-153,219-220);
+ *  - get_shortest_path (minimax.py:64-86) is a FIFO over an ordered SET of (x, y, l) tuples: a cell is marked only when it is
+ *    popped, so a cell can be queued again by a same-level neighbour with a larger l and its distance is then overwritten;
+ *  - get_voronoi_value (minimax.py:88-123) counts cells literally as coded (e.g. enemy-body cells, value -3, count for player 1);
+ *  - a node whose mover has no free neighbour keeps value 0 (minimax.py:233-234, TreeNode value initialised to 0);
+ *  - ties at the root are broken by random.choice, a fully blocked root by random.randint(1,4) (minimax.py:234,267).
+ * tie_mode 0: first best action / action 1 (what the golden fixtures use, with random.choice and randint patched accordingly);
+ * tie_mode 1: Philox-uniform among the best actions. */
+enum { TAG_MINIMAX = 8 };
+#define MM_MAXC 256
+typedef struct { int rows, cols; int16_t v[MM_MAXC]; } mm_map;  /* rows = H+2 (i0), cols = W+2 (i1) */
+
+static int mm_arg(const mm_map* m, int want_max) {
+    int best = 0;
+    for (int i = 1; i < m->rows * m->cols; ++i)
+        if (want_max ? m->v[i] > m->v[best] : m->v[i] < m->v[best]) best = i;
+    return best;
+}
+static inline int mm_wrap(int i, int n) { return i < 0 ? i + n : (i >= n ? n - 1 : i); } /* numpy negative-index wrap; clamp above */
+static inline int mm_at(const mm_map* m, int i0, int i1) { return mm_wrap(i0, m->rows) * m->cols + mm_wrap(i1, m->cols); }
+
+static void mm_shortest_path(const mm_map* gm, int ind, int pl_mi, mm_map* dist) {
+    static const int D0[4] = {0, 1, 0, -1}, D1[4] = {-1, 0, 1, 0}; /* (x,y-1) (x+1,y) (x,y+1) (x-1,y) */
+    int16_t qx[4 * MM_MAXC + 8], qy[4 * MM_MAXC + 8], ql[4 * MM_MAXC + 8];
+    int head = 0, tail = 0;
+    *dist = *gm;
+    qx[tail] = (int16_t)(ind / gm->cols); qy[tail] = (int16_t)(ind % gm->cols); ql[tail] = (int16_t)pl_mi; ++tail;
+    while (head < tail) {
+        const int x = qx[head], y = qy[head], l = ql[head]; ++head;
+        dist->v[mm_at(dist, x, y)] = (int16_t)(l + pl_mi);
+        for (int k = 0; k < 4; ++k) {
+            const int nx = x + D0[k], ny = y + D1[k];
+            if (dist->v[mm_at(dist, nx, ny)] != 1) continue;
+            int dup = 0;
+            for (int q = head; q < tail; ++q) dup |= (qx[q] == nx && qy[q] == ny && ql[q] == l + pl_mi);
+
+            if (!dup && tail < 4 * MM_MAXC + 8) { qx[tail] = (int16_t)nx; qy[tail] = (int16_t)ny; ql[tail] = (int16_t)(l + pl_mi); ++tail; }
+        }
+    }
+}
+static int mm_voronoi(const mm_map* gm, int ind1, int ind2) {
+    mm_map p1, p2;
+    mm_shortest_path(gm, ind1, 1, &p1);
+    mm_shortest_path(gm, ind2, -1, &p2);
+    int a1 = 0, a2 = 0;
+    for (int i = 0; i < gm->rows * gm->cols; ++i) {
+        const int u = p1.v[i], w = p2.v[i];
+        if (u == -1 || u == 2 || w == -2) continue;
+        if (u != 1 && w == 1) a1++;
+        else if (u == 1 && w != 1) a2++;
+        else if (u + w < 0) a1++;
+        else if (u + w > 0) a2++;
+    }
+    return a1 - a2;
+}
+static int mm_blocked(const mm_map* gm, int deo, int blocked[4]) {
+    static const int D0[4] = {0, 1, 0, -1}, D1[4] = {-1, 0, 1, 0};
+    const int ind = mm_arg(gm, deo == 1), x = ind / gm->cols, y = ind % gm->cols;
+    int all = 1;
+    for (int k = 0; k < 4; ++k) {
+        const int v = gm->v[mm_at(gm, x + D0[k], y + D1[k])];
+        blocked[k] = v != 1 ? (v == 10 ? 2 : 1) : 0;
+        if (blocked[k] == 0) all = 0;
+    }
+    return all;
+}
+static void mm_next_map(const mm_map* gm, int action /*0..3*/, int deo, mm_map* out) {
+    static const int D0[4] = {0, 1, 0, -1}, D1[4] = {-1, 0, 1, 0};
+    const int ind = mm_arg(gm, deo == 1), x = ind / gm->cols, y = ind % gm->cols;
+    *out = *gm;
+    out->v[mm_at(out, x + D0[action], y + D1[action])] = (int16_t)(10 * deo);
+    out->v[ind] = -1;
+}
+/* values of the root's children (INT32_MIN for unexpanded moves); returns 1 if the root is fully blocked */
+static int mm_root_values(const mm_map* gm, int value[4]) {
+    int b0[4];
+    for (int k = 0; k < 4; ++k) value[k] = INT32_MIN;
+    if (mm_blocked(gm, 1, b0)) return 1;
+    for (int a = 0; a < 4; ++a) {
+        if (b0[a] == 1) continue;
+        mm_map m1; mm_next_map(gm, a, 1, &m1);
+        int b1[4];
+        if (mm_blocked(&m1, -1, b1)) { value[a] = 0; continue; }
+        int best = INT32_MAX;
+        for (int b = 0; b < 4; ++b) {
+            if (b1[b] == 1) continue;
+            mm_map m2; mm_next_map(&m1, b, -1, &m2);
+            const int v = mm_voronoi(&m2, mm_arg(&m2, 1), mm_arg(&m2, 0));
+            if (v < best) best = v;
+        }
+        value[a] = best;
+    }
+    return 0;
+}
+/* action (0..3) of MinimaxPlayer(2) for `player` (1|2) in every env; values_out [N,4] optional */
+int oracle_minimax_actions(const void* state, int N, int W, int H, int player, int tie_mode, uint64_t seed, uint64_t counter,
+                           uint64_t base, uint8_t* actions, int32_t* values_out) {
+    const int C = cells_of(W, H);
+    if (C > MM_MAXC) return TRON_ERR_UNSUPPORTED;
+    int8_t lut6[6] = {0, 0, 0, 0, 0, 0}, tab[2 * 3 * 8];
+    oracle_build_plane_tables(lut6, TRON_ENC_LUT1, tab);
+    const int8_t* grid = (const int8_t*)state;
+    for (int e = 0; e < N; ++e) {
+        mm_map gm; gm.rows = H + 2; gm.cols = W + 2;
+        for (int r = 0; r < W + 2; ++r)       /* obs[r][c] -> gm[c][r] */
+            for (int c = 0; c < H + 2; ++c)
+                gm.v[c * (W + 2) + r] = tab[(player - 1) * 8 + ((grid[(size_t)e * C + r * (H + 2) + c] + 1) & 7)];
+        int value[4];
+        uint32_t rnd[4];
+        philox4x32_10(seed, counter, base + (uint64_t)e, TAG_MINIMAX, (uint32_t)player, rnd);
+        int act;
+        if (mm_root_values(&gm, value)) {
+            act = tie_mode ? (int)(rnd[0] >> 30) : 0;
+        } else {
+            int best = INT32_MIN, n = 0, list[4];
+            for (int a = 0; a < 4; ++a) if (value[a] != INT32_MIN && value[a] > best) best = value[a];
+            for (int a = 0; a < 4; ++a) if (value[a] == best) list[n++] = a;
+            act = list[tie_mode ? (int)mulhi32(rnd[0], (uint32_t)n) : 0];
+        }
+        actions[e] = (uint8_t)act;
+        if (values_out) for (int a = 0; a < 4; ++a) values_out[4 * e + a] = value[a];
+    }
+    return 0;
+}

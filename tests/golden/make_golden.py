@@ -12,6 +12,7 @@ this path) and writes small fixtures next to this file
   fuzz.json       300 games, W=H in [3,16], random + wall-avoiding policies, per-game SHA-256
   slide.npz       "ice" mode trajectories driven by an explicit Bernoulli tape
   popup.npz       pop_up planes for observations taken from traj.npz
+  minimax.npz     MinimaxPlayer(2, voronoi) decisions + root child values on ~300 mid-game states, both players
   misc.json       get_reward table, get_rate table, replay container semantics, timing of the reference
 
 Usage:  python tests/golden/make_golden.py
@@ -304,6 +305,42 @@ def make_misc(G, U, P):
     return out
 
 
+def make_minimax(G, P, n_states=300, seed=17):
+    """MinimaxPlayer(2, voronoi).action (tron/minimax.py:296-310) on mid-game states from traj.npz, both perspectives.
+    random.choice -> first element, random.randint -> low bound, so ties are deterministic ("tie_mode 0")."""
+    import tron.minimax as tm
+    from tron.map import Map, Tile
+    tr = np.load(os.path.join(HERE, "traj.npz"))
+    live = np.nonzero(tr["done"] == 0)[0]
+    rng = np.random.default_rng(seed)
+    # prefer crowded boards: sort candidates by number of trail cells, take a spread
+    crowd = (tr["tiles"][live] > 0).sum((1, 2))
+    order = live[np.argsort(crowd)]
+    pick = np.unique(np.concatenate([order[-n_states // 2:], rng.choice(order, n_states // 2, replace=False)]))
+    real_choice, real_randint = tm.random.choice, tm.random.randint
+    tiles_out, acts, vals = [], [], []
+    try:
+        tm.random.choice = lambda seq: seq[0]
+        tm.random.randint = lambda a, b: a
+        for row in pick:
+            codes = tr["tiles"][row]
+            m = Map(10, 10, Tile.EMPTY, Tile.WALL)
+            m._data = np.array([[Tile(int(v)) for v in r] for r in codes])
+            a, v = [], []
+            for pid in (1, 2):
+                pl = tm.MinimaxPlayer(2)
+                d = pl.action(m, pid)
+                a.append(d.value - 1)
+                cv = [-(2 ** 31)] * 4
+                for ch in pl.minimax.root._children:
+                    cv[ch.get_action() - 1] = int(ch.get_value())
+                v.append(cv)
+            tiles_out.append(codes); acts.append(a); vals.append(v)
+    finally:
+        tm.random.choice, tm.random.randint = real_choice, real_randint
+    return dict(tiles=np.array(tiles_out, np.int8), actions=np.array(acts, np.uint8), values=np.array(vals, np.int64))
+
+
 def main():
     G, U, P = import_reference()
     kat = make_kat(G, P)
@@ -318,6 +355,7 @@ def main():
     sel = np.linspace(0, tr["obs1"].shape[0] - 1, 64).astype(int)
     np.savez_compressed(os.path.join(HERE, "popup.npz"), obs=tr["obs1"][sel],
                         planes=np.array([U.pop_up(o.astype(np.int64)) for o in tr["obs1"][sel]], np.float32))
+    np.savez_compressed(os.path.join(HERE, "minimax.npz"), **make_minimax(G, P))
     misc = make_misc(G, U, P)
     json.dump(misc, open(os.path.join(HERE, "misc.json"), "w"), indent=1)
     print("reference timing", misc["reference_timing_10x10_random"])

@@ -1,9 +1,12 @@
 // minimax.cu -- batched scripted opponent: the reference's MinimaxPlayer(depth 2, Voronoi heuristic)
 // (tron/minimax.py:58-310) for one player of every game, one warp per game, one lane per (my move, enemy move) leaf.
 //
-// The reference's search is reproduced with its quirks (see oracle/tron_oracle.c for the list): transposed observation,
-// argmax/argmin head lookup, the ordered-set FIFO of get_shortest_path that can overwrite a distance when a cell is queued
-// twice, the literal Voronoi counting rules, value 0 for a mover without free neighbours, first-best / Philox tie-breaks.
+// The reference's search is reproduced with its quirks: it runs on the TRANSPOSED observation of the moving player
+// (minimax.py:298); heads are found with argmax / argmin over the flattened map (:151-153,219-220); get_shortest_path
+// (:64-86) is a FIFO over an ordered SET of (x, y, l) tuples that marks a cell only when it is popped, so a cell can be
+// queued again by a same-level neighbour with a larger l and its distance is then overwritten; get_voronoi_value (:88-123)
+// counts cells literally as coded (enemy-body cells, value -3, count for player 1); a mover without a free neighbour
+// leaves its node at value 0 (:233-234); root ties use first-best or a Philox draw (random.choice / randint, :234,267).
 // Each lane keeps its own map, two distance maps and the BFS queue in local memory (L1-resident, ~5 KB); the 16 leaf
 // values are reduced with shuffles (min over the enemy move, max over my move).  Grids up to 256 cells (W,H <= 14).
 #include "common.cuh"

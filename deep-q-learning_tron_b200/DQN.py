@@ -85,7 +85,7 @@ def train(model=None, n_envs=4096, iterations=100, learn_steps_per_iter=1, devic
             model.zero_grad()
             loss.backward()
             opt.step()
-            losses.append(float(loss))
+            losses.append(float(loss.detach()))
         if log:
             log(it, losses[-1], env.stats_dict())
     return model, losses

@@ -11,7 +11,8 @@ def play_matches(model1, model2=None, n_games=10000, width=10, height=10, gamemo
                  obs_dtype=torch.float32, device="cuda", seed=0, max_ticks=None, spawn_mode="fair"):
     """Play n_games games of model1 (player 1) against model2 (player 2, default: model1).
 
-    A model is anything with `.act(obs[n, P, W+2, H+2]) -> n actions` (like the reference's nets) or a callable doing the same.
+    A model is anything with `.act(obs[n, P, W+2, H+2]) -> n actions` (like the reference's nets), a callable doing the same, or
+    the string "minimax" for the batched scripted opponent (ACKTR.py:409-421 rates the agent against it).
     gamemode None | "ice" | "temper" (tron/game.py:163-178); spawns follow make_game(mode=spawn_mode).
     -> dict(p1_wins, p2_wins, draws, games, mean_ticks, p1_win_rating)   (p1_win_rating = p1/(p1+p2), play.py:94)
     """
@@ -27,14 +28,16 @@ def play_matches(model1, model2=None, n_games=10000, width=10, height=10, gamemo
     act = torch.empty((n_games, 2), dtype=torch.uint8, device=env.device)
     limit = max_ticks or (width * height + 2)
 
-    def choose(m, o):
+    def choose(m, o, player):
+        if isinstance(m, str) and m == "minimax":  # the reference's scripted opponent, MinimaxPlayer(2, "voronoi")
+            return env.minimax_actions(player)
         a = m.act(o) if hasattr(m, "act") else m(o)
         return torch.as_tensor(a, device=env.device).reshape(-1).to(torch.uint8)
 
     ticks = 0
     while ticks < limit:
-        act[:, 0] = choose(model1, obs[:, 0])
-        act[:, 1] = choose(model2, obs[:, 1])
+        act[:, 0] = choose(model1, obs[:, 0], 1)
+        act[:, 1] = choose(model2, obs[:, 1], 2)
         res = env.step(act, obs=obs)
         ticks += 1
         if ticks % 4 == 0 and bool(res.done.all()):  # finished games stay frozen, so one flag read every few ticks suffices

@@ -143,7 +143,8 @@ def run_reference(a):
     from oracle import py_port
     t0 = time.perf_counter()
     s, _ = py_port.play_random(0, 300, W, W)
-    per = max(200, int(2.5 * s / (time.perf_counter() - t0)))
+    rate1 = s / (time.perf_counter() - t0)
+    per = max(200, int(min(2.5, 120.0 / max(a.steps, 1)) * rate1))  # ~2.5 s of work per core per step, whole run bounded to ~2 min
     for _ in range(a.warmup):
         cpu_py_port(W, max(50, per // 8), cores)
     total, dt = 0, 0.0

@@ -66,14 +66,22 @@ def train(model=None, n_envs=4096, iterations=100, learn_steps_per_iter=1, devic
     obs = env.reset()
     epsilon = float(EPSILON_START)
     losses = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_fwd = t_env = 0.0
     for it in range(iterations):
         for _ in range(GAME_CYCLE):
+            ev[0].record()
             with torch.no_grad():
                 q = model(obs.view(2 * n_envs, 1, 12, 12))
+            ev[1].record()
             act = env.select_actions(q, epsilon, counter=env.counter)
             res = env.step(act)
             mem.push_batch(obs.view(2 * n_envs, 1, 12, 12), act.view(-1), res.obs.view(2 * n_envs, 1, 12, 12), res.reward.view(-1), res.done, done_stride=2)
             obs = res.obs
+            ev[2].record()
+            if log:
+                torch.cuda.synchronize()
+                t_fwd += ev[0].elapsed_time(ev[1]); t_env += ev[1].elapsed_time(ev[2])
             if epsilon * DECAY_RATE > ESPILON_END:
                 epsilon *= DECAY_RATE
         for _ in range(learn_steps_per_iter):
@@ -87,5 +95,7 @@ def train(model=None, n_envs=4096, iterations=100, learn_steps_per_iter=1, devic
             opt.step()
             losses.append(float(loss.detach()))
         if log:
-            log(it, losses[-1], env.stats_dict())
+            st = env.stats_dict()
+            st.update(q_forward_ms_per_tick=t_fwd / ((it + 1) * GAME_CYCLE), env_replay_ms_per_tick=t_env / ((it + 1) * GAME_CYCLE))
+            log(it, losses[-1], st)
     return model, losses

@@ -25,7 +25,18 @@ if __name__ == "__main__":
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--ticks", type=int, default=40)
     ap.add_argument("--learn-every", type=int, default=4)
+    ap.add_argument("--algo", default="ddqn", choices=["ddqn", "dqn"], help="ddqn: DDQN.py loop (pop_up obs); dqn: DQN.py survivor loop (1-plane obs)")
     a = ap.parse_args()
+    if a.algo == "dqn":  # BASELINE config #3 as worded: DQN.py survivor loop, GPU replay, batched self-play
+        import DQN
+        out = []
+        model, losses = DQN.train(n_envs=a.envs, iterations=max(1, a.ticks // DQN.GAME_CYCLE), log=lambda it, loss, st: out.append((loss, st)))
+        loss, st = out[-1]
+        print(json.dumps({"config": "DQN survivor loop (DQN.py:135-309 restated), %d envs, 1-plane f32 obs, GPU replay ring" % a.envs,
+                          "ms_per_tick": {"q_forward(2N obs)": st["q_forward_ms_per_tick"], "select+env_step+replay_push": st["env_replay_ms_per_tick"]},
+                          "env_fraction_of_tick": st["env_replay_ms_per_tick"] / (st["env_replay_ms_per_tick"] + st["q_forward_ms_per_tick"]),
+                          "loss": loss, "episodes": st["episodes"], "mean_episode_ticks": st["ep_ticks"] / max(1, st["episodes"])}))
+        sys.exit(0)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     logs = []

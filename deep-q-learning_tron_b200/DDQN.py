@@ -69,10 +69,15 @@ class Agent:
             for p in list(self.qnetwork_local.parameters()) + list(self.qnetwork_target.parameters()):
                 dist.broadcast(p.data, 0)
 
-    def q_values(self, obs):
+    def q_values(self, obs, amp=False):
+        """acting forward; amp=True runs it under bf16 autocast (cuDNN/cuBLAS tensor-core paths, observations are already bf16)"""
         self.qnetwork_local.eval()
         with torch.no_grad():
-            q = self.qnetwork_local(obs)
+            if amp:
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    q = self.qnetwork_local(obs).float()
+            else:
+                q = self.qnetwork_local(obs)
         self.qnetwork_local.train()
         return q
 
@@ -113,7 +118,8 @@ def allreduce_gradients(model):
         off += n
 
 
-def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloat16, learn_every=UPDATE_EVERY, data_parallel=None, log=None):
+def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloat16, learn_every=UPDATE_EVERY, data_parallel=None, log=None,
+          amp=False):
     """Batched DDQN loop (DDQN.py:206-346 restated): every tick both players of all envs act epsilon-greedily from the
     local net, 2*n_envs transitions go into the GPU ring, and every `learn_every` ticks one Double-DQN learn step runs.
     Under torchrun each rank owns n_envs envs (env_id_base = rank * n_envs) and gradients are all-reduced."""
@@ -138,7 +144,7 @@ def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloa
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     for t in range(env_steps):
         ev[0].record()
-        q = agent.q_values(obs.view(2 * n_envs, 3, 12, 12))
+        q = agent.q_values(obs.view(2 * n_envs, 3, 12, 12), amp=amp)
         ev[1].record()
         act = env.select_actions(q, epsilon, counter=env.counter)
         res = env.step(act)

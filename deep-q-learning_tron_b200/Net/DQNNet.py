@@ -31,7 +31,9 @@ class Net(nn.Module):
         return x * torch.tanh(F.softplus(x))
 
     def forward(self, x):
-        x = x.to(self.conv1.weight.device, self.conv1.weight.dtype)
+        x = x.to(self.conv1.weight.device)
+        if not torch.is_autocast_enabled():
+            x = x.to(self.conv1.weight.dtype)
         x = self.activation(self.conv1(x))
         skip = x
         x = self.activation(self.conv2(x))

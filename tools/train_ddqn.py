@@ -25,6 +25,7 @@ if __name__ == "__main__":
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--ticks", type=int, default=40)
     ap.add_argument("--learn-every", type=int, default=4)
+    ap.add_argument("--amp", action="store_true", help="bf16 autocast for the acting forward")
     ap.add_argument("--algo", default="ddqn", choices=["ddqn", "dqn"], help="ddqn: DDQN.py loop (pop_up obs); dqn: DQN.py survivor loop (1-plane obs)")
     a = ap.parse_args()
     if a.algo == "dqn":  # BASELINE config #3 as worded: DQN.py survivor loop, GPU replay, batched self-play
@@ -40,13 +41,13 @@ if __name__ == "__main__":
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     logs = []
-    agent, env = DDQN.train(n_envs=a.envs, env_steps=a.ticks, learn_every=a.learn_every, log=lambda t, d: logs.append(d))
+    agent, env = DDQN.train(n_envs=a.envs, env_steps=a.ticks, learn_every=a.learn_every, log=lambda t, d: logs.append(d), amp=a.amp)
     warm = logs[len(logs) // 4:]
     fw = sum(d["forward_ms"] for d in warm) / len(warm); er = sum(d["env_replay_ms"] for d in warm) / len(warm)
     lr = sum(d["learn_ms"] for d in warm) / len(warm)
     st = env.stats_dict()
     if rank == 0:
-        print(json.dumps({"config": "DDQN self-play, %d envs/GPU x %d GPU(s), pop_up bf16 obs, GPU replay ring" % (a.envs, world),
+        print(json.dumps({"config": "DDQN self-play, %d envs/GPU x %d GPU(s), pop_up bf16 obs, GPU replay ring%s" % (a.envs, world, ", bf16 autocast forward" if a.amp else ""),
                           "ms_per_tick": {"q_forward(2N obs)": fw, "select+env_step+replay_push": er, "sample+learn(+allreduce)": lr},
                           "env_fraction_of_tick": er / (fw + er + lr), "env_steps_per_s_per_gpu": a.envs / ((fw + er + lr) * 1e-3),
                           "loss": logs[-1]["loss"], "episodes": st["episodes"], "mean_episode_ticks": st["ep_ticks"] / max(1, st["episodes"]),

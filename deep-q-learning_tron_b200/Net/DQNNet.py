@@ -28,7 +28,7 @@ class Net(nn.Module):
 
     @staticmethod
     def mish(x):
-        return x * torch.tanh(F.softplus(x))
+        return F.mish(x)  # == x * tanh(softplus(x)) (Net/ACNet.py:56-57), as one fused PyTorch kernel instead of three
 
     def forward(self, x):
         x = x.to(self.conv1.weight.device)

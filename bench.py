@@ -36,7 +36,8 @@ def parse():
     ap.add_argument("--width", type=int, default=10)
     ap.add_argument("--obs-dtype", default="bf16", choices=["bf16", "f32", "i8"])
     ap.add_argument("--enc", default="lut1", choices=["lut1", "popup3", "popup3_const", "none"])
-    ap.add_argument("--layout", default="bits10", choices=["bits10", "tile8"], help="state layout: 32-byte bit planes (10x10 only) or int8 Tile.value grid")
+    ap.add_argument("--layout", default="bits10", choices=["bits10", "tile8", "trail"],
+                    help="state layout: 32-byte bit planes (10x10 only), int8 Tile.value grid, or trail-list records (pure ticks only)")
     ap.add_argument("--e2e-steps", type=int, default=6)
     ap.add_argument("--sustained-seconds", type=float, default=1.0, help="extra untimed-for-the-headline run of the same step (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the cpu_baseline leg")
@@ -274,6 +275,8 @@ def run_ours(a):
     b_o = {"bf16": 2, "f32": 4, "i8": 1}[a.obs_dtype]
     M = 48
     grid_bytes = 32 if a.layout == "bits10" else C  # state bytes per game as stored (C * b_g)
+    if a.layout == "trail":
+        grid_bytes = 0  # a reset writes nothing but the 16-byte header
     if P:
         bytes_per_env_step = grid_bytes * (1 + f_reset) + 2 * P * C * b_o + M
     else:  # pure tick: <=4 sectors read+written, one metadata sector each way, reset amortisation
@@ -291,7 +294,7 @@ def run_ours(a):
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "step_bits10_kernel" if a.layout == "bits10" else ("step_sparse_kernel" if (not P and C >= 1024) else "step_tile_kernel"), "state_bytes_per_game": grid_bytes, "bytes_per_env_step": bytes_per_env_step, "reset_fraction": f_reset,
+                "peak_source": peak_src, "kernel": "step_bits10_kernel" if a.layout == "bits10" else ("step_trail_kernel" if a.layout == "trail" else "step_sparse_kernel" if (not P and C >= 1024) else "step_tile_kernel"), "state_bytes_per_game": grid_bytes, "bytes_per_env_step": bytes_per_env_step, "reset_fraction": f_reset,
                 "envs_per_launch": N, "launch_ms": launch_ms, "frac_of_8TBs_nominal": achieved / 8000.0}
 
     # e2e: the same workload through the host-buffer C-ABI front end (pinned host arrays in, host arrays out)

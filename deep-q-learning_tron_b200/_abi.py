@@ -18,6 +18,7 @@ U8, I32, I64, BF16, F32, I8 = 0, 1, 2, 3, 4, 5
 ENC_NONE, ENC_LUT1, ENC_POPUP3, ENC_POPUP3_CONST = 0, 1, 2, 3
 LAYOUT_TILE8 = 0
 LAYOUT_BITS10 = 1
+LAYOUT_TRAIL = 2
 OPT_SPARSE_MIN_CELLS = 1
 OPT_TILE_BYTES = 2
 SLIDE_NONE, SLIDE_TAPE, SLIDE_ICE, SLIDE_TEMPER = 0, 1, 2, 3
@@ -102,6 +103,8 @@ def dtype_size(dt):
 
 def state_bytes(n_envs, width, height, layout=LAYOUT_TILE8):
     per = 32 if layout == LAYOUT_BITS10 else cells_per_env(width, height)
+    if layout == LAYOUT_TRAIL:
+        per = max(64, (16 + 4 * width * height + 15) & ~15)
     grid = (n_envs * per + 255) & ~255
     meta = (8 * n_envs + 255) & ~255
     return grid + meta + 8 * n_envs

@@ -16,7 +16,7 @@ _TORCH_OF = {abi.BF16: torch.bfloat16, abi.F32: torch.float32, abi.I8: torch.int
 _CODE_OF = {torch.bfloat16: abi.BF16, torch.float32: abi.F32, torch.int8: abi.I8, torch.uint8: abi.U8,
             torch.int32: abi.I32, torch.int64: abi.I64}
 _ENC_OF = {"none": abi.ENC_NONE, "lut1": abi.ENC_LUT1, "popup3": abi.ENC_POPUP3, "popup3_const": abi.ENC_POPUP3_CONST}
-_LAYOUT_OF = {"tile8": abi.LAYOUT_TILE8, "bits10": abi.LAYOUT_BITS10}
+_LAYOUT_OF = {"tile8": abi.LAYOUT_TILE8, "bits10": abi.LAYOUT_BITS10, "trail": abi.LAYOUT_TRAIL}
 _SLIDE_OF = {None: abi.SLIDE_NONE, "tape": abi.SLIDE_TAPE, "ice": abi.SLIDE_ICE, "temper": abi.SLIDE_TEMPER}
 
 
@@ -283,7 +283,7 @@ class BatchedTron:
     def minimax_actions(self, player, tie_mode=1, counter=None, out=None, want_values=False):
         """The move (0..3) the reference's MinimaxPlayer(2, voronoi) would make for `player` (1|2) in every game
         (tron/minimax.py:296-310).  tie_mode 0 = first best move, 1 = uniform among the best (Philox)."""
-        tiles = self.state if self.layout == abi.LAYOUT_TILE8 else self.export()["tiles"]
+        tiles = self.state if self.layout == abi.LAYOUT_TILE8 else self.export()["tiles"].contiguous()
         if out is None:
             out = torch.empty(self.N, dtype=torch.uint8, device=self.device)
         vals = torch.empty((self.N, 4), dtype=torch.int32, device=self.device) if want_values else None

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libtron_b200.so")
-SOURCES = ["abi.cu", "step_c144.cu", "step_generic.cu", "step_sparse.cu", "step_bits10.cu", "minimax.cu", "misc_kernels.cu"]
+SOURCES = ["abi.cu", "step_c144.cu", "step_generic.cu", "step_sparse.cu", "step_bits10.cu", "step_trail.cu", "minimax.cu", "misc_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
 

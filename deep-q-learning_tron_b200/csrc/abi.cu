@@ -14,9 +14,12 @@ namespace {
 
 inline size_t align256(size_t x) { return (x + 255u) & ~(size_t)255u; }
 inline bool geometry_ok(int n, int w, int h) { return n > 0 && w >= 2 && h >= 2 && w <= 126 && h <= 126; }
-inline bool layout_ok(int layout, int w, int h) { return layout == TRON_LAYOUT_TILE8 || (layout == TRON_LAYOUT_BITS10 && w == 10 && h == 10); }
+inline bool layout_known(int layout) { return layout == TRON_LAYOUT_TILE8 || layout == TRON_LAYOUT_BITS10 || layout == TRON_LAYOUT_TRAIL; }
+inline bool layout_ok(int layout, int w, int h) { return layout == TRON_LAYOUT_TILE8 || layout == TRON_LAYOUT_TRAIL || (layout == TRON_LAYOUT_BITS10 && w == 10 && h == 10); }
 // bytes of grid state per game
-inline size_t grid_stride(int layout, int w, int h) { return layout == TRON_LAYOUT_BITS10 ? 32u : (size_t)(w + 2) * (size_t)(h + 2); }
+inline size_t grid_stride(int layout, int w, int h) {
+    return layout == TRON_LAYOUT_BITS10 ? 32u : layout == TRON_LAYOUT_TRAIL ? trail_record_bytes_host(w, h) : (size_t)(w + 2) * (size_t)(h + 2);
+}
 inline int planes_of(int enc) { return enc == TRON_ENC_LUT1 ? 1 : enc == TRON_ENC_POPUP3 ? 3 : enc == TRON_ENC_POPUP3_CONST ? 4 : 0; }
 inline int enc_kind_of(int enc) { return enc == TRON_ENC_LUT1 ? 1 : enc == TRON_ENC_POPUP3 ? 2 : enc == TRON_ENC_POPUP3_CONST ? 3 : 0; }
 
@@ -50,8 +53,9 @@ void build_device_tables(const int8_t lut6[6], int enc, int obs_dtype, PlaneTab 
 int fill_params(const tron_step_args* a, int mode, StepParams& p) {
     if (!a || a->struct_size != sizeof(tron_step_args)) return TRON_ERR_INVALID;
     if (!geometry_ok(a->n_envs, a->width, a->height) || !a->state) return TRON_ERR_INVALID;
-    if (a->layout != TRON_LAYOUT_TILE8 && a->layout != TRON_LAYOUT_BITS10) return TRON_ERR_INVALID;
+    if (!layout_known(a->layout)) return TRON_ERR_INVALID;
     if (!layout_ok(a->layout, a->width, a->height)) return TRON_ERR_UNSUPPORTED;
+    if (a->layout == TRON_LAYOUT_TRAIL && (a->obs_enc != TRON_ENC_NONE || mode == MODE_OBSERVE)) return TRON_ERR_UNSUPPORTED;
     if (a->layout == TRON_LAYOUT_BITS10 && mode == MODE_STEP && a->slide_mode != TRON_SLIDE_NONE) return TRON_ERR_UNSUPPORTED;
     if (((uintptr_t)a->state & 15u) != 0) return TRON_ERR_ALIGN;
     memset(&p, 0, sizeof p);
@@ -98,6 +102,7 @@ namespace {
 int dispatch(StepParams& p, int mode, int obs_dtype, int obs_enc, cudaStream_t s) {
     const int kind = enc_kind_of(obs_enc);
     if (p.layout == TRON_LAYOUT_BITS10) return launch_step_bits10(p, mode, obs_dtype, kind, s);
+    if (p.layout == TRON_LAYOUT_TRAIL) return launch_step_trail(p, mode, s);
     if (mode == MODE_STEP && kind == 0 && p.C >= g_sparse_min_cells) return launch_step_sparse(p, s);
     if (p.C == 144 && p.Hc == 12) { p.G = tile_envs_c144(); return launch_step_c144(p, mode, obs_dtype, kind, s); }
     p.G = tile_envs_generic(p.C);
@@ -132,7 +137,7 @@ int tron_enc_planes(int obs_enc) { return planes_of(obs_enc); }
 int tron_dtype_size(int dtype) { return tron_elem(dtype); }
 
 int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* grid_off, size_t* meta_off, size_t* boxes_off) {
-    if (!geometry_ok(n_envs, width, height) || (layout != TRON_LAYOUT_TILE8 && layout != TRON_LAYOUT_BITS10)) return TRON_ERR_INVALID;
+    if (!geometry_ok(n_envs, width, height) || !layout_known(layout)) return TRON_ERR_INVALID;
     if (!layout_ok(layout, width, height)) return TRON_ERR_UNSUPPORTED;
     const size_t mo = align256((size_t)n_envs * grid_stride(layout, width, height));
     if (grid_off) *grid_off = 0;
@@ -224,6 +229,7 @@ int tron_export_grid(const void* state, int n_envs, int width, int height, int l
     const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo, nullptr);
     if (rc != TRON_OK || !state) return rc != TRON_OK ? rc : TRON_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
+    if (layout == TRON_LAYOUT_TRAIL) return launch_trail_export(state, n_envs, width, height, tiles, heads, alive, done, winner, ep_len, s);
     if (tiles && layout == TRON_LAYOUT_BITS10) {
         if (launch_bits10_export(state, (const char*)state + mo, n_envs, tiles, s) != TRON_OK) return TRON_ERR_CUDA;
     } else if (tiles && cudaMemcpyAsync(tiles, state, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
@@ -238,6 +244,7 @@ int tron_import_grid(void* state, int n_envs, int width, int height, int layout,
     const int rc = tron_state_offsets(n_envs, width, height, layout, nullptr, &mo, nullptr);
     if (rc != TRON_OK || !state) return rc != TRON_OK ? rc : TRON_ERR_INVALID;
     cudaStream_t s = (cudaStream_t)stream;
+    if (layout == TRON_LAYOUT_TRAIL) return launch_trail_import(state, n_envs, width, height, tiles, heads, alive, done, winner, ep_len, s);
     if (tiles && layout == TRON_LAYOUT_BITS10) {
         if (launch_bits10_import(state, n_envs, tiles, s) != TRON_OK) return TRON_ERR_CUDA;
     } else if (tiles && cudaMemcpyAsync(state, tiles, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {

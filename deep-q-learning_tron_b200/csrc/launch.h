@@ -18,6 +18,12 @@ __host__ __device__ inline int tron_elem(int dt) {
 int launch_step_c144(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_step_generic(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_step_sparse(const StepParams& p, cudaStream_t s);
+int launch_step_trail(const StepParams& p, int mode, cudaStream_t s);
+size_t trail_record_bytes_host(int W, int H);
+int launch_trail_export(const void* recs, int n, int W, int H, int8_t* tiles, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner,
+                        int32_t* ep_len, cudaStream_t s);
+int launch_trail_import(void* recs, int n, int W, int H, const int8_t* tiles, const int8_t* heads, const uint8_t* alive, const uint8_t* done,
+                        const uint8_t* winner, const int32_t* ep_len, cudaStream_t s);
 int launch_step_bits10(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_bits10_export(const void* planes, const void* meta, int n, int8_t* tiles, cudaStream_t s);
 int launch_bits10_import(void* planes, int n, const int8_t* tiles, cudaStream_t s);

@@ -1,0 +1,196 @@
+// step_trail.cu -- pure tick for LARGE grids on a TRAIL-LIST state (TRON_LAYOUT_TRAIL).
+//
+// A dense 64x64 grid is 4,356 B per game of which a tick touches ~6 cells scattered over several DRAM rows; the int8
+// sparse kernel is therefore bound by random 32-byte DRAM operations (~15 per game-tick), not by bandwidth.  Here a game
+// is ONE record whose hot part is contiguous:
+//     [0:8)   tron_meta (heads, alive/done/winner flags, ep_len)      [8:10) n1   [10:12) n2   [12:16) reserved
+//     [16: )  trail cells, interleaved by player: entry (k, player) at 16 + 2*(2k + player), 2 bytes = {p0 | slide<<7, p1}
+// Every tile a player leaves behind (body, or slide tile in ice/temper mode) is appended to its list; walls are implicit
+// and heads live in the meta.  "Is this cell free?" is a scan of both lists -- a handful of entries for typical episodes --
+// and a reset is n1 = n2 = 0.  The first 12 ticks of both players sit in the record's first 64 bytes, so a game-tick is
+// normally one 64-byte read and one or two sector writes.  Capacity is W*H entries per player (trail cells are distinct
+// interior cells), so the representation is exact for any episode; tron_export_grid renders the Tile.value grid.
+// Observations are not produced from this layout (use TRON_LAYOUT_TILE8 / BITS10 for the fused obs path).
+#include "launch.h"
+#include "tick_core.cuh"
+
+namespace tron {
+
+constexpr int kTrailThreads = 128;
+constexpr int kTrailHot = 24;  // entries held in registers (bytes 16..64 of the record)
+
+// 16-byte aligned and at least 64 bytes (the kernel always loads the first 64)
+__host__ __device__ inline size_t trail_record_bytes(int W, int H) {
+    const size_t r = (16u + 4u * (size_t)W * (size_t)H + 15u) & ~(size_t)15u;
+    return r < 64u ? 64u : r;
+}
+size_t trail_record_bytes_host(int W, int H) { return trail_record_bytes(W, H); }
+
+struct TrailCells {
+    unsigned char* rec;       // this game's record in HBM
+    int n[2];                 // entries per player at the start of the tick (those are in hot[] / HBM)
+    uint32_t hot[kTrailHot / 2];  // first 24 entries as loaded
+    unsigned short fresh[4];  // entries appended during this tick (two bodies, up to two slide tiles)
+    int fresh_owner[4], n_fresh;
+    int W, H;
+
+    __device__ __forceinline__ static unsigned short pack(int r, int c, bool slide) { return (unsigned short)((r & 0x7F) | (slide ? 0x80 : 0) | (c << 8)); }
+
+    __device__ __forceinline__ int get(int r, int c) const {
+        if (r < 0 || c < 0 || r >= W || c >= H) return TRON_TILE_WALL;
+        const unsigned key = (unsigned)(r & 0x7F) | ((unsigned)c << 8);
+        bool hit = false;
+#pragma unroll
+        for (int w = 0; w < kTrailHot / 2; ++w) {  // word w = {entry (k=w, P1), entry (k=w, P2)}
+            const unsigned e1 = hot[w] & 0xFF7Fu, e2 = (hot[w] >> 16) & 0xFF7Fu;
+            hit |= (w < n[0] && e1 == key) | (w < n[1] && e2 == key);
+        }
+        const int nmax = max(n[0], n[1]);
+        if (nmax > kTrailHot / 2) {  // long episode: the rest of the lists, straight from memory
+            const uint32_t* words = (const uint32_t*)(rec + 16);
+            for (int w = kTrailHot / 2; w < nmax; ++w) {
+                const uint32_t v = words[w];
+                hit |= (w < n[0] && (v & 0xFF7Fu) == key) | (w < n[1] && ((v >> 16) & 0xFF7Fu) == key);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hit |= (i < n_fresh && (fresh[i] & 0xFF7Fu) == key);
+        return hit ? TRON_TILE_P1_BODY : TRON_TILE_EMPTY;  // callers only test for EMPTY
+    }
+    __device__ __forceinline__ void put(int r, int c, int tile) {
+        int owner;
+        bool slide = false;
+        if (tile == TRON_TILE_P1_BODY) owner = 0;
+        else if (tile == TRON_TILE_P2_BODY) owner = 1;
+        else if (tile == TRON_TILE_P1_SLIDE) { owner = 0; slide = true; }
+        else if (tile == TRON_TILE_P2_SLIDE) { owner = 1; slide = true; }
+        else return;  // heads are metadata
+        if (r < 0 || c < 0 || r >= W || c >= H) return;  // a head that left the board leaves no trail tile there
+        int cnt = n[owner];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cnt += (i < n_fresh && fresh_owner[i] == owner);
+        const unsigned short e = pack(r, c, slide);
+        ((unsigned short*)(rec + 16))[2 * cnt + owner] = e;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i == n_fresh) { fresh[i] = e; fresh_owner[i] = owner; }
+        n_fresh = min(n_fresh + 1, 4);
+    }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTrailThreads) step_trail_kernel(const StepParams p) {
+    const int tid = threadIdx.x;
+    const long long env = (long long)blockIdx.x * kTrailThreads + tid;
+    if (env >= p.N) return;
+    const size_t R = trail_record_bytes(p.W, p.H);
+    unsigned char* rec = (unsigned char*)p.grid + (size_t)env * R;
+    uint4 hdr = *(const uint4*)rec;
+    EnvState e = unpack_meta(make_uint2(hdr.x, hdr.y));
+    TrailCells g;
+    g.rec = rec; g.W = p.W; g.H = p.H;
+    g.n[0] = (int)(hdr.z & 0xFFFFu); g.n[1] = (int)(hdr.z >> 16);
+    const int T = MODE == MODE_STEP ? p.T : 1;
+    for (int t = 0; t < T; ++t) {
+        if (MODE == MODE_STEP) {
+            const uint4 a = *(const uint4*)(rec + 16), b = *(const uint4*)(rec + 32), c = *(const uint4*)(rec + 48);
+            g.hot[0] = a.x; g.hot[1] = a.y; g.hot[2] = a.z; g.hot[3] = a.w; g.hot[4] = b.x; g.hot[5] = b.y; g.hot[6] = b.z; g.hot[7] = b.w;
+            g.hot[8] = c.x; g.hot[9] = c.y; g.hot[10] = c.z; g.hot[11] = c.w;
+        }
+        g.n_fresh = 0;
+        BoxRegs bx;
+        const bool do_reset = env_tick<MODE, false>(g, p, e, env, t, tid, bx);
+        if (do_reset) { g.n[0] = g.n[1] = 0; }
+        else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (i < g.n_fresh) g.n[g.fresh_owner[i]] += 1;
+        }
+        if (T > 1) __threadfence_block();  // this thread re-reads its own appended entries on the next tick
+    }
+    const uint2 m = pack_meta(e);
+    *(uint4*)rec = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
+}
+
+int launch_step_trail(const StepParams& p, int mode, cudaStream_t s) {
+    const unsigned grid = (unsigned)(((long long)p.N + kTrailThreads - 1) / kTrailThreads);
+    if (mode == MODE_STEP) step_trail_kernel<MODE_STEP><<<grid, kTrailThreads, 0, s>>>(p);
+    else if (mode == MODE_RESET) step_trail_kernel<MODE_RESET><<<grid, kTrailThreads, 0, s>>>(p);
+    else return TRON_ERR_UNSUPPORTED;
+    return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
+}
+
+// ---- export: render Tile.value grids / metadata from the records; import: rebuild the lists from grids ---------------
+__global__ void trail_export_kernel(const unsigned char* __restrict__ recs, int n, int W, int H, int8_t* tiles, int8_t* heads, uint8_t* alive,
+                                    uint8_t* done, uint8_t* winner, int32_t* ep_len) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    const size_t R = trail_record_bytes(W, H);
+    const unsigned char* rec = recs + (size_t)env * R;
+    const uint4 hdr = *(const uint4*)rec;
+    const EnvState e = unpack_meta(make_uint2(hdr.x, hdr.y));
+    const int n1 = (int)(hdr.z & 0xFFFFu), n2 = (int)(hdr.z >> 16), Hc = H + 2, C = (W + 2) * (H + 2);
+    if (tiles) {
+        int8_t* t = tiles + (size_t)env * C;
+        for (int c = 0; c < C; ++c) {
+            const int r = c / Hc, q = c - r * Hc;
+            t[c] = (r == 0 || r == W + 1 || q == 0 || q == H + 1) ? (int8_t)TRON_TILE_WALL : (int8_t)TRON_TILE_EMPTY;
+        }
+        const unsigned short* ent = (const unsigned short*)(rec + 16);
+        for (int k = 0; k < max(n1, n2); ++k)
+            for (int pl = 0; pl < 2; ++pl) {
+                if (k >= (pl ? n2 : n1)) continue;
+                const unsigned short v = ent[2 * k + pl];
+                const int r = v & 0x7F, c = v >> 8;
+                const bool slide = v & 0x80;
+                t[(r + 1) * Hc + c + 1] = (int8_t)(pl ? (slide ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY) : (slide ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY));
+            }
+        t[(e.r1 + 1) * Hc + e.c1 + 1] = TRON_TILE_P1_HEAD;
+        t[(e.r2 + 1) * Hc + e.c2 + 1] = TRON_TILE_P2_HEAD;  // written second (reference game.py:205-214)
+    }
+    if (heads) ((uint32_t*)heads)[env] = hdr.x;
+    if (alive) { alive[2 * env] = e.flags & 1u; alive[2 * env + 1] = (e.flags >> 1) & 1u; }
+    if (done) done[env] = (e.flags >> 2) & 1u;
+    if (winner) winner[env] = (e.flags >> TRON_FLAG_WINNER_SHIFT) & 3u;
+    if (ep_len) ep_len[env] = e.k;
+}
+__global__ void trail_import_kernel(unsigned char* recs, int n, int W, int H, const int8_t* __restrict__ tiles, const int8_t* heads, const uint8_t* alive,
+                                    const uint8_t* done, const uint8_t* winner, const int32_t* ep_len) {
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= n) return;
+    const size_t R = trail_record_bytes(W, H);
+    unsigned char* rec = recs + (size_t)env * R;
+    uint4 hdr = *(const uint4*)rec;
+    if (tiles) {
+        const int Hc = H + 2;
+        const int8_t* t = tiles + (size_t)env * (W + 2) * (H + 2);
+        unsigned short* ent = (unsigned short*)(rec + 16);
+        int n1 = 0, n2 = 0;
+        for (int r = 0; r < W; ++r)
+            for (int c = 0; c < H; ++c) {
+                const int v = t[(r + 1) * Hc + c + 1];
+                if (v == TRON_TILE_P1_BODY || v == TRON_TILE_P1_SLIDE) ent[2 * (n1++) + 0] = TrailCells::pack(r, c, v == TRON_TILE_P1_SLIDE);
+                else if (v == TRON_TILE_P2_BODY || v == TRON_TILE_P2_SLIDE) ent[2 * (n2++) + 1] = TrailCells::pack(r, c, v == TRON_TILE_P2_SLIDE);
+            }
+        hdr.z = (uint32_t)n1 | ((uint32_t)n2 << 16);
+    }
+    uint32_t f = hdr.y & 0xFFu, k = hdr.y >> 16;
+    if (heads) hdr.x = ((const uint32_t*)heads)[env];
+    if (alive) f = (f & ~3u) | (alive[2 * env] ? 1u : 0u) | (alive[2 * env + 1] ? 2u : 0u);
+    if (done) f = (f & ~TRON_FLAG_DONE) | (done[env] ? TRON_FLAG_DONE : 0u);
+    if (winner) f = (f & ~(3u << TRON_FLAG_WINNER_SHIFT)) | ((winner[env] & 3u) << TRON_FLAG_WINNER_SHIFT);
+    if (ep_len) k = (uint32_t)ep_len[env] & 0xFFFFu;
+    hdr.y = f | (k << 16);
+    *(uint4*)rec = hdr;
+}
+int launch_trail_export(const void* recs, int n, int W, int H, int8_t* tiles, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner,
+                        int32_t* ep_len, cudaStream_t s) {
+    trail_export_kernel<<<(n + 127) / 128, 128, 0, s>>>((const unsigned char*)recs, n, W, H, tiles, heads, alive, done, winner, ep_len);
+    return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
+}
+int launch_trail_import(void* recs, int n, int W, int H, const int8_t* tiles, const int8_t* heads, const uint8_t* alive, const uint8_t* done,
+                        const uint8_t* winner, const int32_t* ep_len, cudaStream_t s) {
+    trail_import_kernel<<<(n + 127) / 128, 128, 0, s>>>((unsigned char*)recs, n, W, H, tiles, heads, alive, done, winner, ep_len);
+    return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
+}
+
+}  // namespace tron

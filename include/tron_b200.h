@@ -78,8 +78,11 @@ enum {
 /* state layouts */
 enum {
     TRON_LAYOUT_TILE8 = 0, /* int8 Tile.value per cell (any grid size, all modes) + 8-byte meta + 8-byte dirty boxes per env */
-    TRON_LAYOUT_BITS10 = 1 /* 10x10 grids only, no slide modes: two 128-bit planes (trail occupancy, trail owner) over the
+    TRON_LAYOUT_BITS10 = 1, /* 10x10 grids only, no slide modes: two 128-bit planes (trail occupancy, trail owner) over the
                               100 interior cells = 32 bytes per game; walls implicit, heads in the meta.  4.5x less state traffic. */
+    TRON_LAYOUT_TRAIL = 2  /* any grid, pure ticks only (TRON_ENC_NONE; tron_observe unsupported): one record per game = 16-byte
+                              header + the list of trail cells both players left behind (capacity W*H each, 2 bytes per cell).
+                              A game-tick touches the record's first 64 bytes instead of scattered cells of a dense grid. */
 };
 
 /* RNG spawn rules of make_game (tron/util.py:46-84) */
@@ -136,7 +139,7 @@ typedef struct tron_step_args {
     uint32_t struct_size; /* sizeof(tron_step_args) */
     int32_t n_envs;       /* N */
     int32_t width, height;
-    int32_t layout;       /* TRON_LAYOUT_TILE8 | TRON_LAYOUT_BITS10 */
+    int32_t layout;       /* TRON_LAYOUT_TILE8 | TRON_LAYOUT_BITS10 | TRON_LAYOUT_TRAIL */
     void* state;          /* device, tron_state_bytes() bytes, 256-byte aligned */
 
     const void* actions;  /* device [N,2] (P1,P2) values 0..3, or NULL -> uniform random policy from (seed,counter) */

@@ -71,6 +71,8 @@ def main():
     run("10x10 pure step (no obs)", 4 * M, 10, "bf16", "none")
     run("64x64 bf16 1-plane", 128 * 1024, 64, "bf16", "lut1", steps=10)
     run("64x64 pure step (config #5, 2M envs/GPU)", 2 * M, 64, "bf16", "none", steps=10)
+    run("64x64 pure step, trail-list state", 2 * M, 64, "bf16", "none", steps=20, layout="trail")
+    run("64x64 pure step, trail-list state, in-kernel policy", 2 * M, 64, "bf16", "none", steps=20, layout="trail", actions="rng")
     if not quick:
         run("10x10 bf16, 65,536 envs (config #3 size)", 65536, 10, "bf16", "popup3", steps=200)
         run("10x10 bf16, 4,096 envs (config #2 size, launch-bound)", 4096, 10, "bf16", "lut1", steps=500)

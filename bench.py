@@ -281,6 +281,8 @@ def run_ours(a):
         bytes_per_env_step = grid_bytes * (1 + f_reset) + 2 * P * C * b_o + M
     else:  # pure tick: <=4 sectors read+written, one metadata sector each way, reset amortisation
         bytes_per_env_step = 320 + f_reset * grid_bytes
+        if a.layout == "trail":
+            bytes_per_env_step = 64 + 64 + 16  # record head read + written back, actions + reward/done/winner
     launch_ms = ms / a.steps
     achieved = bytes_per_env_step * N / (launch_ms * 1e-3) / 1e9
     peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"

@@ -45,6 +45,8 @@ def run(name, N, W, dtype, enc, steps=20, warmup=3, actions="tape", auto_reset=T
         B = (32 if layout == "bits10" else C) * (1 + f) + 2 * P * C * b_o + 48
     else:
         B = 320 + f * C  # SURVEY 8d pure-step sector model
+        if layout == "trail":
+            B = 64 + 64 + 16  # one 64-byte record head read + written back, actions + reward/done/winner
     rate = N / (ms * 1e-3)
     out = dict(case=name, layout=layout, envs=N, grid=W, obs=dtype, enc=enc, ms_per_step=ms, env_steps_per_s=rate, reset_fraction=f, bytes_per_env_step=B,
                achieved_GBps=rate * B / 1e9, frac_of_measured_peak=rate * B / 1e9 / PEAK)

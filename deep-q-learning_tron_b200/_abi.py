@@ -104,7 +104,7 @@ def dtype_size(dt):
 def state_bytes(n_envs, width, height, layout=LAYOUT_TILE8):
     per = 32 if layout == LAYOUT_BITS10 else cells_per_env(width, height)
     if layout == LAYOUT_TRAIL:
-        per = max(64, (16 + 4 * width * height + 15) & ~15)
+        per = (16 + 4 * width * height + 63) & ~63
     grid = (n_envs * per + 255) & ~255
     meta = (8 * n_envs + 255) & ~255
     return grid + meta + 8 * n_envs

@@ -19,11 +19,9 @@ namespace tron {
 constexpr int kTrailThreads = 128;
 constexpr int kTrailHot = 24;  // entries held in registers (bytes 16..64 of the record)
 
-// 16-byte aligned and at least 64 bytes (the kernel always loads the first 64)
-__host__ __device__ inline size_t trail_record_bytes(int W, int H) {
-    const size_t r = (16u + 4u * (size_t)W * (size_t)H + 15u) & ~(size_t)15u;
-    return r < 64u ? 64u : r;
-}
+// a multiple of 64 bytes: the hot head of a record (header + first 24 entries) is then exactly one 64-byte DRAM atom /
+// two L2 sectors, and the kernel may always load the first 64 bytes
+__host__ __device__ inline size_t trail_record_bytes(int W, int H) { return (16u + 4u * (size_t)W * (size_t)H + 63u) & ~(size_t)63u; }
 size_t trail_record_bytes_host(int W, int H) { return trail_record_bytes(W, H); }
 
 struct TrailCells {
@@ -79,7 +77,7 @@ struct TrailCells {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kTrailThreads) step_trail_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kTrailThreads, 8) step_trail_kernel(const StepParams p) {
     const int tid = threadIdx.x;
     const long long env = (long long)blockIdx.x * kTrailThreads + tid;
     if (env >= p.N) return;

@@ -55,7 +55,6 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
     if (!geometry_ok(a->n_envs, a->width, a->height) || !a->state) return TRON_ERR_INVALID;
     if (!layout_known(a->layout)) return TRON_ERR_INVALID;
     if (!layout_ok(a->layout, a->width, a->height)) return TRON_ERR_UNSUPPORTED;
-    if (a->layout == TRON_LAYOUT_TRAIL && (a->obs_enc != TRON_ENC_NONE || mode == MODE_OBSERVE)) return TRON_ERR_UNSUPPORTED;
     if (a->layout == TRON_LAYOUT_BITS10 && mode == MODE_STEP && a->slide_mode != TRON_SLIDE_NONE) return TRON_ERR_UNSUPPORTED;
     if (((uintptr_t)a->state & 15u) != 0) return TRON_ERR_ALIGN;
     memset(&p, 0, sizeof p);
@@ -102,7 +101,7 @@ namespace {
 int dispatch(StepParams& p, int mode, int obs_dtype, int obs_enc, cudaStream_t s) {
     const int kind = enc_kind_of(obs_enc);
     if (p.layout == TRON_LAYOUT_BITS10) return launch_step_bits10(p, mode, obs_dtype, kind, s);
-    if (p.layout == TRON_LAYOUT_TRAIL) return launch_step_trail(p, mode, s);
+    if (p.layout == TRON_LAYOUT_TRAIL) return (kind == 0 || mode == MODE_RESET) ? launch_step_trail(p, mode, s) : launch_step_trail_obs(p, mode, obs_dtype, kind, s);
     if (mode == MODE_STEP && kind == 0 && p.C >= g_sparse_min_cells) return launch_step_sparse(p, s);
     if (p.C == 144 && p.Hc == 12) { p.G = tile_envs_c144(); return launch_step_c144(p, mode, obs_dtype, kind, s); }
     p.G = tile_envs_generic(p.C);

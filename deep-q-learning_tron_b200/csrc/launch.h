@@ -19,6 +19,7 @@ int launch_step_c144(const StepParams& p, int mode, int obs_dtype, int enc_kind,
 int launch_step_generic(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_step_sparse(const StepParams& p, cudaStream_t s);
 int launch_step_trail(const StepParams& p, int mode, cudaStream_t s);
+int launch_step_trail_obs(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 size_t trail_record_bytes_host(int W, int H);
 int launch_trail_export(const void* recs, int n, int W, int H, int8_t* tiles, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner,
                         int32_t* ep_len, cudaStream_t s);

@@ -12,7 +12,7 @@
 // interior cells), so the representation is exact for any episode; tron_export_grid renders the Tile.value grid.
 // Observations are not produced from this layout (use TRON_LAYOUT_TILE8 / BITS10 for the fused obs path).
 #include "launch.h"
-#include "tick_core.cuh"
+#include "step_kernels.cuh"
 
 namespace tron {
 
@@ -107,6 +107,128 @@ __global__ void __launch_bounds__(kTrailThreads, 8) step_trail_kernel(const Step
     }
     const uint2 m = pack_meta(e);
     *(uint4*)rec = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
+}
+
+// ---- fused tick + observation planes on the trail-list state (large grids) -------------------------------------------
+// CTA = 128 threads, G games (G*C <= ~18 KB of shared memory).  Threads 0..G-1 tick their game on its record; then the
+// whole CTA renders the G grids into shared memory (template fill, 16-byte stores), the owners scatter their trail
+// entries and heads, and encode_tile() streams both players' planes out.  Compared with the int8 layout this skips the
+// C-byte grid read and the C-byte write-back per game-tick (8.7 KB of 26 KB at 64x64 bf16).
+template <int OD, int LP, bool CP, int CH, int MODE>
+__global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = p.C, G = p.G, Hc = p.Hc, tid = threadIdx.x;
+    int8_t* tile = (int8_t*)smem_raw;                       // [G][C]
+    int8_t* tmpl = tile + ((G * C + 15) & ~15);             // [C]
+    const long long env0 = (long long)blockIdx.x * G;
+    const int nG = (int)min((long long)G, (long long)p.N - env0);
+    for (int c = tid; c < C; c += kTrailThreads) {
+        const int r = c / Hc, q = c - r * Hc;
+        tmpl[c] = (r == 0 || r == p.W + 1 || q == 0 || q == p.H + 1) ? (int8_t)TRON_TILE_WALL : (int8_t)TRON_TILE_EMPTY;
+    }
+    const bool owner = tid < nG;
+    const long long env = env0 + tid;
+    const size_t R = trail_record_bytes(p.W, p.H);
+    unsigned char* rec = (unsigned char*)p.grid + (size_t)(owner ? env : env0) * R;
+    EnvState e = unpack_meta(make_uint2(0, 0));
+    TrailCells g;
+    g.rec = rec; g.W = p.W; g.H = p.H; g.n[0] = g.n[1] = 0;
+    if (owner) {
+        const uint4 hdr = *(const uint4*)rec;
+        e = unpack_meta(make_uint2(hdr.x, hdr.y));
+        g.n[0] = (int)(hdr.z & 0xFFFFu); g.n[1] = (int)(hdr.z >> 16);
+    }
+    __syncthreads();
+    const int T = MODE == MODE_STEP ? p.T : 1;
+    for (int t = 0; t < T; ++t) {
+        if (MODE == MODE_STEP && owner) {
+            const uint4 a = *(const uint4*)(rec + 16), b = *(const uint4*)(rec + 32), c = *(const uint4*)(rec + 48);
+            g.hot[0] = a.x; g.hot[1] = a.y; g.hot[2] = a.z; g.hot[3] = a.w; g.hot[4] = b.x; g.hot[5] = b.y; g.hot[6] = b.z; g.hot[7] = b.w;
+            g.hot[8] = c.x; g.hot[9] = c.y; g.hot[10] = c.z; g.hot[11] = c.w;
+            g.n_fresh = 0;
+            BoxRegs bx;
+            if (env_tick<MODE_STEP, false>(g, p, e, env, t, tid, bx)) { g.n[0] = g.n[1] = 0; }
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < g.n_fresh) g.n[g.fresh_owner[i]] += 1;
+            }
+        }
+        if (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1) {
+            // render: template for every game, then the owners scatter their trails and heads
+            if ((C & 15) == 0) {
+                const int per = C / 16;
+                for (int it = tid; it < nG * per; it += kTrailThreads) { const int ee = it / per; ((uint4*)(tile + ee * C))[it - ee * per] = ((const uint4*)tmpl)[it - ee * per]; }
+            } else if ((C & 3) == 0) {
+                const int per = C / 4;
+                for (int it = tid; it < nG * per; it += kTrailThreads) { const int ee = it / per; ((uint32_t*)(tile + ee * C))[it - ee * per] = ((const uint32_t*)tmpl)[it - ee * per]; }
+            } else {
+                for (int it = tid; it < nG * C; it += kTrailThreads) tile[it] = tmpl[it % C];
+            }
+            __syncthreads();
+            if (owner) {
+                int8_t* tl = tile + tid * C;
+                const unsigned short* ent = (const unsigned short*)(rec + 16);
+                const int nmax = max(g.n[0], g.n[1]);
+                for (int k = 0; k < nmax; ++k) {
+                    const uint32_t v = ((const uint32_t*)ent)[k];
+                    if (k < g.n[0]) { const unsigned u = v & 0xFFFFu; tl[((u & 0x7F) + 1) * Hc + (u >> 8) + 1] = (u & 0x80) ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY; }
+                    if (k < g.n[1]) { const unsigned u = v >> 16; tl[((u & 0x7F) + 1) * Hc + (u >> 8) + 1] = (u & 0x80) ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY; }
+                }
+                tl[(e.r1 + 1) * Hc + e.c1 + 1] = TRON_TILE_P1_HEAD;
+                tl[(e.r2 + 1) * Hc + e.c2 + 1] = TRON_TILE_P2_HEAD;
+            }
+            __syncthreads();
+            encode_tile<0, kTrailThreads, OD, LP, CP, CH>(tile, nG, env0, p, (MODE == MODE_STEP && p.obs_every_tick) ? t : 0);
+            if (T > 1) __syncthreads();
+        }
+    }
+    if (MODE == MODE_STEP && owner) {
+        const uint2 m = pack_meta(e);
+        *(uint4*)rec = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
+    }
+}
+
+template <int OD, int LP, bool CP, int MODE>
+static int launch_trail_obs_one(StepParams p, cudaStream_t s) {
+    // games per CTA: ~18 KB of tile like the int8 generic kernel
+    int G = (int)(18432 / p.C);
+    G = G < 1 ? 1 : (G > kTrailThreads ? kTrailThreads : G);
+    p.G = G;
+    const size_t smem = (size_t)((G * p.C + 15) & ~15) + (size_t)((p.C + 15) & ~15);
+    const unsigned grid = (unsigned)(((long long)p.N + G - 1) / G);
+    if ((p.C & 3) == 0) {
+        auto k = step_trail_obs_kernel<OD, LP, CP, 4, MODE>;
+        static size_t lim = 48 * 1024;
+        if (smem > lim) { if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TRON_ERR_CUDA; lim = smem; }
+        k<<<grid, kTrailThreads, smem, s>>>(p);
+    } else {
+        auto k = step_trail_obs_kernel<OD, LP, CP, 1, MODE>;
+        static size_t lim = 48 * 1024;
+        if (smem > lim) { if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TRON_ERR_CUDA; lim = smem; }
+        k<<<grid, kTrailThreads, smem, s>>>(p);
+    }
+    return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
+}
+template <int OD, int MODE>
+static int launch_trail_obs_enc(const StepParams& p, int enc_kind, cudaStream_t s) {
+    switch (enc_kind) {
+        case 1: return launch_trail_obs_one<OD, 1, false, MODE>(p, s);
+        case 2: return launch_trail_obs_one<OD, 3, false, MODE>(p, s);
+        case 3: return launch_trail_obs_one<OD, 3, true, MODE>(p, s);
+        default: return TRON_ERR_INVALID;
+    }
+}
+int launch_step_trail_obs(const StepParams& p, int mode, int od, int enc_kind, cudaStream_t s) {
+    if (mode == MODE_STEP) {
+        if (od == TRON_BF16) return launch_trail_obs_enc<TRON_BF16, MODE_STEP>(p, enc_kind, s);
+        if (od == TRON_F32) return launch_trail_obs_enc<TRON_F32, MODE_STEP>(p, enc_kind, s);
+        if (od == TRON_I8) return launch_trail_obs_enc<TRON_I8, MODE_STEP>(p, enc_kind, s);
+    } else if (mode == MODE_OBSERVE) {
+        if (od == TRON_BF16) return launch_trail_obs_enc<TRON_BF16, MODE_OBSERVE>(p, enc_kind, s);
+        if (od == TRON_F32) return launch_trail_obs_enc<TRON_F32, MODE_OBSERVE>(p, enc_kind, s);
+        if (od == TRON_I8) return launch_trail_obs_enc<TRON_I8, MODE_OBSERVE>(p, enc_kind, s);
+    }
+    return TRON_ERR_INVALID;
 }
 
 int launch_step_trail(const StepParams& p, int mode, cudaStream_t s) {

@@ -80,9 +80,9 @@ enum {
     TRON_LAYOUT_TILE8 = 0, /* int8 Tile.value per cell (any grid size, all modes) + 8-byte meta + 8-byte dirty boxes per env */
     TRON_LAYOUT_BITS10 = 1, /* 10x10 grids only, no slide modes: two 128-bit planes (trail occupancy, trail owner) over the
                               100 interior cells = 32 bytes per game; walls implicit, heads in the meta.  4.5x less state traffic. */
-    TRON_LAYOUT_TRAIL = 2  /* any grid, pure ticks only (TRON_ENC_NONE; tron_observe unsupported): one record per game = 16-byte
-                              header + the list of trail cells both players left behind (capacity W*H each, 2 bytes per cell).
-                              A game-tick touches the record's first 64 bytes instead of scattered cells of a dense grid. */
+    TRON_LAYOUT_TRAIL = 2  /* any grid, all modes: one record per game = 16-byte header + the list of trail cells both players
+                              left behind (capacity W*H each, 2 bytes per cell).  A game-tick touches the record's first 64
+                              bytes instead of a dense grid; observations are rendered in shared memory.  Made for large grids. */
 };
 
 /* RNG spawn rules of make_game (tron/util.py:46-84) */

@@ -115,9 +115,29 @@ def test_trail_import_export_and_cross_layout():
         assert np.array_equal(c.export()[k], v), k
 
 
-def test_trail_refuses_observations():
-    from tron_b200 import _lib
-    from tron_b200.batch_env import BatchedTron
-    env = BatchedTron(8, 10, 10, layout=L, obs_enc="lut1")
-    with pytest.raises(_lib.TronError):
-        env.reset()
+@pytest.mark.parametrize("W,N,dt,enc", [(64, 300, abi.BF16, abi.ENC_LUT1), (10, 4096, abi.BF16, abi.ENC_POPUP3), (7, 777, abi.F32, abi.ENC_LUT1),
+                                         (31, 500, abi.I8, abi.ENC_POPUP3_CONST), (126, 9, abi.BF16, abi.ENC_LUT1), (12, 1000, abi.F32, abi.ENC_POPUP3)])
+def test_trail_fused_observations_match_oracle(W, N, dt, enc):
+    g, o = make_pair(N, W, W, layout=L, obs_dtype=dt, obs_enc=enc, const_plane=5.0, seed=80 + W, slide_mode=abi.SLIDE_ICE, slide_rate=0.2)
+    assert np.array_equal(g.reset(), o.reset())
+    for t in range(30):
+        assert_same_step(g.step(), o.step(), "W=%d tick %d" % (W, t))
+    assert_same_state(g, o)
+    assert np.array_equal(g.observe(), o.observe())
+    assert_same_step(g.step_many(6), o.step_many(6))
+    assert_same_step(g.step_many(6, obs_every_tick=False), o.step_many(6, obs_every_tick=False))
+    assert_same_state(g, o)
+
+
+def test_trail_explicit_tapes_config2_shape():
+    N = 4096
+    rng = np.random.default_rng(0)
+    g, o = make_pair(N, 10, 10, layout=L, obs_dtype=abi.BF16, obs_enc=abi.ENC_LUT1)
+    sp = rng.integers(0, 10, size=(N, 4)).astype(np.int8); sp[:, 2] = (sp[:, 0] + 1 + rng.integers(0, 9, N)) % 10
+    assert np.array_equal(g.reset(spawn=sp), o.reset(spawn=sp))
+    for t in range(64):
+        act = rng.integers(0, 4, size=(N, 2)).astype(np.uint8)
+        sp = rng.integers(0, 10, size=(N, 4)).astype(np.int8); sp[:, 2] = (sp[:, 0] + 1 + rng.integers(0, 9, N)) % 10
+        assert_same_step(g.step(act, spawn=sp), o.step(act, spawn=sp), "tick %d" % t)
+    assert_same_state(g, o)
+    assert np.array_equal(g.stats, o.stats)

@@ -43,6 +43,8 @@ def run(name, N, W, dtype, enc, steps=20, warmup=3, actions="tape", auto_reset=T
     b_o = {"bf16": 2, "f32": 4, "i8": 1}[dtype]
     if P:
         B = (32 if layout == "bits10" else C) * (1 + f) + 2 * P * C * b_o + 48
+        if layout == "trail":
+            B = 128 + 2 * P * C * b_o + 48
     else:
         B = 320 + f * C  # SURVEY 8d pure-step sector model
         if layout == "trail":
@@ -72,6 +74,8 @@ def main():
     run("10x10 bf16 pop_up + const plane", 2 * M, 10, "bf16", "popup3_const")
     run("10x10 pure step (no obs)", 4 * M, 10, "bf16", "none")
     run("64x64 bf16 1-plane", 128 * 1024, 64, "bf16", "lut1", steps=10)
+    run("64x64 bf16 1-plane, trail-list state", 128 * 1024, 64, "bf16", "lut1", steps=10, layout="trail")
+    run("32x32 bf16 1-plane, trail-list state", 512 * 1024, 32, "bf16", "lut1", steps=10, layout="trail")
     run("64x64 pure step (config #5, 2M envs/GPU)", 2 * M, 64, "bf16", "none", steps=10)
     run("64x64 pure step, trail-list state", 2 * M, 64, "bf16", "none", steps=20, layout="trail")
     run("64x64 pure step, trail-list state, in-kernel policy", 2 * M, 64, "bf16", "none", steps=20, layout="trail", actions="rng")

@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
     const uint32_t tile_bytes = (uint32_t)(nG * C);
     const bool bulk_ok = (tile_bytes & 15u) == 0 && ((((uintptr_t)gsrc) & 15u) == 0);
     const bool need_load = !(MODE == MODE_RESET && p.env_mask == nullptr);
+    // large grids: a tick changes <= 6 of the C bytes, so only those (or a rebuilt game) go back to HBM
+    const bool sparse_wb = C_T == 0 && MODE == MODE_STEP && C >= 1024;
 
     if (tid == 0 && bulk_ok && need_load) mbar_init(bar, 1);
     __syncthreads();
@@ -180,8 +182,19 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
             if (owner) {
                 EnvState e = unpack_meta(mraw);
                 BoxRegs bx;
-                ByteCells cells{tile + tid * C, p.Hc};
-                const bool do_reset = env_tick<MODE, false>(cells, p, e, env, t, tid, bx);
+                bool do_reset;
+                if (C_T == 0 && sparse_wb) {  // large grids: remember the <=6 bytes this tick changes, write only those back
+                    LoggedByteCells cells{tile + tid * C, p.Hc, 0, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+                    do_reset = env_tick<MODE, false>(cells, p, e, env, t, tid, bx);
+                    if (!do_reset) {
+                        int8_t* gg = p.grid + (size_t)env * C;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) if (k < cells.n) gg[cells.idx[k]] = cells.val[k];
+                    }
+                } else {
+                    ByteCells cells{tile + tid * C, p.Hc};
+                    do_reset = env_tick<MODE, false>(cells, p, e, env, t, tid, bx);
+                }
                 if (MODE == MODE_RESET && do_reset && p.boxes) {  // a fresh grid has exactly two non-template cells
                     box_set_spawn(bx, e);
                     p.boxes[env] = pack_boxes(bx);
@@ -224,10 +237,26 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
                     }
                 }
             }
-            if (t == T - 1) fence_proxy_async();
+            if (t == T - 1 && !sparse_wb) fence_proxy_async();
             __syncthreads();
             // ------------------------------------------------------------ write the tile back (last tick only)
-            if (t == T - 1) {
+            if (sparse_wb) {  // changed bytes already went out in phase 1; rebuilt games are written whole, every tick
+                if ((C & 3) == 0) {
+                    const int per = C / 4;
+                    for (int e = 0; e < nG; ++e) {
+                        if (!rflag[e]) continue;
+                        uint32_t* gd = (uint32_t*)(p.grid + (size_t)(env0 + e) * C);
+                        const uint32_t* sd = (const uint32_t*)(tile + e * C);
+                        for (int ch = tid; ch < per; ch += NT) gd[ch] = sd[ch];
+                    }
+                } else {
+                    for (int e = 0; e < nG; ++e) {
+                        if (!rflag[e]) continue;
+                        for (int ch = tid; ch < C; ch += NT) p.grid[(size_t)(env0 + e) * C + ch] = tile[e * C + ch];
+                    }
+                }
+                if (t == T - 1 && owner) p.meta[env] = mraw;
+            } else if (t == T - 1) {
                 int8_t* gdst = p.grid + env0 * C;
                 if (bulk_ok) {
                     if (tid == 0) { bulk_s2g(gdst, tile, tile_bytes); bulk_commit(); }
@@ -242,7 +271,7 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
             encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, (MODE == MODE_STEP && p.obs_every_tick) ? t : 0);
         if (T > 1) __syncthreads();  // next tick's phase 1 rewrites the tile
     }
-    if (MODE != MODE_OBSERVE && bulk_ok && tid == 0) bulk_wait_read_all();  // tile must outlive the bulk store's read
+    if (MODE != MODE_OBSERVE && bulk_ok && !sparse_wb && tid == 0) bulk_wait_read_all();  // tile must outlive the bulk store's read
 }
 
 }  // namespace tron

@@ -90,6 +90,25 @@ struct ByteCells {  // int8 Tile.value grid, row-major (W+2) x (H+2), in shared 
     __device__ __forceinline__ void put(int r, int c, int tile) { p[(r + 1) * Hc + c + 1] = (int8_t)tile; }
 };
 
+// ByteCells that also remembers what it wrote (at most two bodies, two slide tiles, two heads per tick), so that a kernel
+// holding the grid in shared memory can write back just those bytes instead of the whole grid.
+struct LoggedByteCells {
+    int8_t* p;
+    int Hc;
+    int n;
+    unsigned short idx[6];
+    int8_t val[6];
+    __device__ __forceinline__ int get(int r, int c) const { return p[(r + 1) * Hc + c + 1]; }
+    __device__ __forceinline__ void put(int r, int c, int tile) {
+        const int i = (r + 1) * Hc + c + 1;
+        p[i] = (int8_t)tile;
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k == n) { idx[k] = (unsigned short)i; val[k] = (int8_t)tile; }
+        n = min(n + 1, 6);
+    }
+};
+
 // One tick of the env whose cells start at `g`.  Updates `e` (fresh game state if it returns true = "rebuild this grid"),
 // writes reward/done/winner/ep_len for (tick t, env) and adds to the striped statistics.  TRACK maintains the dirty boxes.
 template <int MODE, bool TRACK, class Cells>

@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-streams", dest="streams", action="store_false", help="skip the epsilon-greedy action-stream lines")
     return ap.parse_args()
 
 
@@ -333,6 +334,30 @@ def run_ours(a):
             e2e["int8_obs_variant"] = {"value": sum_over_ranks(float(N * a.e2e_steps)) / dt8, "unit": UNIT, "d2h_bytes_per_step": N * (2 * P * C + 10)}
             h8.close()
 
+    # epsilon-greedy action streams (SURVEY 8d proxy computed in-kernel: with prob. eps uniform, else a random FREE neighbour): fewer resets
+    streams = None
+    if rank == 0 and a.streams:
+        streams = []
+        for eps in (1.0, 0.5, 0.1, 0.003):
+            env_e = BatchedTron(N, W, W, device=dev, obs_dtype=tdt, obs_enc=a.enc, reward="ddqn", seed=3, layout=a.layout, policy="free_eps", policy_epsilon=eps)
+            obs_e = env_e.reset()
+            for i in range(40):  # let episode lengths reach their stationary mix
+                env_e.step(obs=obs_e, reward=reward, done=done, winner=winner, want_ep_len=False)
+            torch.cuda.synchronize()
+            q0 = env_e.stats_dict()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(a.steps):
+                env_e.step(obs=obs_e, reward=reward, done=done, winner=winner, want_ep_len=False)
+            e1.record(); torch.cuda.synchronize()
+            q1 = env_e.stats_dict()
+            fe = (q1["episodes"] - q0["episodes"]) / (q1["env_steps"] - q0["env_steps"])
+            be = (grid_bytes * (1 + fe) + 2 * P * C * b_o + M) if P else bytes_per_env_step
+            rate = N * a.steps / (e0.elapsed_time(e1) * 1e-3)
+            streams.append({"epsilon": eps, "value": rate, "unit": UNIT, "reset_fraction": fe, "bytes_per_env_step": be, "frac_of_peak": rate * be / 1e9 / peak})
+            del env_e, obs_e
+            torch.cuda.empty_cache()
+
     # launch-bound regime of the literal config #2 size: 4096 envs, T ticks per launch (tron_step_many)
     small = None
     if rank == 0:
@@ -371,7 +396,7 @@ def run_ours(a):
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic", "config": workload_config(a, N),
-               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": a.steps, "clocks": clocks, "sustained": sustained, "small_n": small,
+               "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": a.steps, "clocks": clocks, "sustained": sustained, "eps_greedy_streams": streams, "small_n": small,
                "episode_stats": {"reset_fraction": f_reset, "mean_episode_ticks": (st1["ep_ticks"] - st0["ep_ticks"]) / max(1, st1["episodes"] - st0["episodes"])}}
         print(json.dumps(out))
     if world > 1:

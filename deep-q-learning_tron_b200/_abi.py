@@ -23,6 +23,7 @@ OPT_SPARSE_MIN_CELLS = 1
 OPT_TILE_BYTES = 2
 SLIDE_NONE, SLIDE_TAPE, SLIDE_ICE, SLIDE_TEMPER = 0, 1, 2, 3
 SPAWN_UNIFORM, SPAWN_FAIR = 0, 1
+POLICY_UNIFORM, POLICY_FREE_EPS = 0, 1
 STATS_SLOTS, STATS_FIELDS = 64, 8
 (STAT_EPISODES, STAT_P1_WINS, STAT_P2_WINS, STAT_DRAWS, STAT_EP_TICKS, STAT_BAD_ACTION,
  STAT_ENV_STEPS) = range(7)
@@ -61,6 +62,7 @@ class StepArgs(C.Structure):
         ("slide_mode", C.c_int32), ("slide_rate", C.c_float), ("slide_tape", C.c_void_p),
         ("slide_params", C.c_void_p),
         ("stats", C.c_void_p),
+        ("policy", C.c_int32), ("policy_epsilon", C.c_float),
         ("n_ticks", C.c_int32), ("obs_every_tick", C.c_int32),
     ]
 

@@ -43,11 +43,14 @@ class BatchedTron:
 
     def __init__(self, n_envs, width=10, height=10, device="cuda", obs_dtype=torch.bfloat16, obs_enc="lut1", lut=None,
                  const_plane=0.0, reward="ddqn", auto_reset=True, seed=0, env_id_base=0, slide_mode=None,
-                 slide_rate=0.15, collect_stats=True, layout="tile8", spawn_mode="uniform"):
+                 slide_rate=0.15, collect_stats=True, layout="tile8", spawn_mode="uniform",
+                 policy="uniform", policy_epsilon=0.0):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.layout = _LAYOUT_OF[layout] if isinstance(layout, str) else int(layout)
         self.spawn_mode = {"uniform": abi.SPAWN_UNIFORM, "fair": abi.SPAWN_FAIR}[spawn_mode] if isinstance(spawn_mode, str) else int(spawn_mode)
+        self.policy = {"uniform": abi.POLICY_UNIFORM, "free_eps": abi.POLICY_FREE_EPS}[policy] if isinstance(policy, str) else int(policy)
+        self.policy_epsilon = float(policy_epsilon)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.TronError("BatchedTron needs a CUDA device; there is no CPU fallback")
@@ -111,6 +114,7 @@ class BatchedTron:
                               obs_dtype=self.obs_dtype, obs_enc=self.obs_enc, lut=self.lut, const_plane=self.const_plane,
                               reward_table=self.reward_table, auto_reset=int(self.auto_reset), seed=self.seed,
                               env_id_base=self.env_id_base, slide_mode=self.slide_mode, slide_rate=self.slide_rate, spawn_mode=self.spawn_mode,
+                              policy=self.policy, policy_epsilon=self.policy_epsilon,
                               slide_params=_ptr(self.slide_params), stats=_ptr(self.stats))
         for k, v in kw.items():
             setattr(a, k, v)

@@ -85,6 +85,8 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
         p.auto_reset = a->auto_reset; p.slide_mode = a->slide_mode;
         if (a->spawn_mode != TRON_SPAWN_UNIFORM && a->spawn_mode != TRON_SPAWN_FAIR) return TRON_ERR_INVALID;
         p.ice_thr = (long long)((double)a->slide_rate * 16777216.0);
+        if (a->policy != TRON_POLICY_UNIFORM && a->policy != TRON_POLICY_FREE_EPS) return TRON_ERR_INVALID;
+        p.eps_thr = a->policy == TRON_POLICY_FREE_EPS ? (long long)((double)a->policy_epsilon * 16777216.0) : -1;
         p.r_base = a->reward_table.step_base; p.r_tick = a->reward_table.step_per_tick;
         p.r_win = a->reward_table.win; p.r_lose = a->reward_table.lose; p.r_draw = a->reward_table.draw;
     }

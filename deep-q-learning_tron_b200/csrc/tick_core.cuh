@@ -30,6 +30,7 @@ struct StepParams {
     unsigned long long seed, counter, env_base;
     const unsigned long long* counter_dev;
     long long ice_thr;
+    long long eps_thr;  // TRON_POLICY_FREE_EPS: explore iff 24-bit mantissa <= eps_thr; < 0 -> uniform policy
     int N, W, H, Hc, C, G, layout;
     int T, obs_every_tick, auto_reset, slide_mode, action_dtype, spawn_mode;
     int P;  // planes written per player (lut planes + optional const plane)
@@ -127,6 +128,30 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
         } else {
             const uint4 r = philox(p.seed, ctr, genv, TAG_ACTION, 0);
             a1 = (int)(r.x >> 30); a2 = (int)(r.y >> 30);
+            if (p.eps_thr >= 0 && !(e.flags & TRON_FLAG_DONE)) {  // epsilon-greedy proxy: a random FREE neighbour unless exploring
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const uint32_t w = i ? r.y : r.x;
+                    int& act = i ? a2 : a1;
+                    act = (int)(w & 3u);
+                    if ((long long)(w >> 8) <= p.eps_thr) continue;
+                    const int hr = i ? e.r2 : e.r1, hc = i ? e.c2 : e.c1;
+                    int free_mask = 0, n_free = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = hr + (k == 2) - (k == 0), cc = hc + (k == 1) - (k == 3);
+                        const bool fr = rr >= 0 && cc >= 0 && rr < p.W && cc < p.H && g.get(rr, cc) == TRON_TILE_EMPTY &&
+                                        !(rr == e.r1 && cc == e.c1) && !(rr == e.r2 && cc == e.c2);
+                        free_mask |= fr ? (1 << k) : 0; n_free += fr;
+                    }
+                    if (n_free) {
+                        int pick = (int)__umulhi(i ? r.w : r.z, (uint32_t)n_free);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if ((free_mask >> k) & 1) { if (pick == 0) act = k; --pick; }
+                    }
+                }
+            }
         }
         float rw0 = 0.f, rw1 = 0.f;
         uint32_t done = 0, winner = 0;

@@ -91,6 +91,13 @@ enum {
     TRON_SPAWN_FAIR = 1     /* P1 in the clipped 3x3 box around a random point, P2 in the point-mirrored box (util.py:48-62) */
 };
 
+/* built-in synthetic policies for benchmark action streams (actions == NULL) */
+enum {
+    TRON_POLICY_UNIFORM = 0,  /* iid uniform{0..3} ("random policy") */
+    TRON_POLICY_FREE_EPS = 1  /* epsilon-greedy proxy: with probability epsilon uniform{0..3}, else a uniformly random FREE
+                                 neighbour cell of the own head if one exists, else uniform */
+};
+
 /* slide ("ice"/"temper") modes, tron/game.py:163-178 */
 enum {
     TRON_SLIDE_NONE = 0,
@@ -142,7 +149,7 @@ typedef struct tron_step_args {
     int32_t layout;       /* TRON_LAYOUT_TILE8 | TRON_LAYOUT_BITS10 | TRON_LAYOUT_TRAIL */
     void* state;          /* device, tron_state_bytes() bytes, 256-byte aligned */
 
-    const void* actions;  /* device [N,2] (P1,P2) values 0..3, or NULL -> uniform random policy from (seed,counter) */
+    const void* actions;  /* device [N,2] (P1,P2) values 0..3, or NULL -> built-in synthetic policy (see `policy`) from (seed,counter) */
     int32_t action_dtype; /* TRON_U8 | TRON_I32 | TRON_I64 */
 
     void* obs;            /* device [N,2,P,W+2,H+2], 16-byte aligned, or NULL when obs_enc == TRON_ENC_NONE */
@@ -174,6 +181,9 @@ typedef struct tron_step_args {
     int8_t* slide_params;       /* device [N,4] {degree, weight1, weight2, 0} for TRON_SLIDE_TEMPER; re-drawn on auto-reset */
 
     uint64_t* stats;      /* device [TRON_STATS_SLOTS*TRON_STATS_FIELDS] or NULL */
+
+    int32_t policy;       /* used when actions == NULL: TRON_POLICY_UNIFORM | TRON_POLICY_FREE_EPS */
+    float policy_epsilon; /* TRON_POLICY_FREE_EPS: probability of a uniform move */
 
     /* tron_step_many only */
     int32_t n_ticks;      /* T */

@@ -59,7 +59,7 @@ class OracleEnv:
 
     def __init__(self, n_envs, width=10, height=10, obs_dtype=abi.BF16, obs_enc=abi.ENC_LUT1, lut=None,
                  const_plane=0.0, reward="ddqn", auto_reset=True, seed=0, env_id_base=0,
-                 slide_mode=abi.SLIDE_NONE, slide_rate=0.0, spawn_mode=0):
+                 slide_mode=abi.SLIDE_NONE, slide_rate=0.0, spawn_mode=0, policy=0, policy_epsilon=0.0):
         self.N, self.W, self.H = n_envs, width, height
         self.C = abi.cells_per_env(width, height)
         self.P = abi.enc_planes(obs_enc)
@@ -70,6 +70,7 @@ class OracleEnv:
         self.auto_reset, self.seed, self.env_id_base = int(auto_reset), seed, env_id_base
         self.slide_mode, self.slide_rate = slide_mode, slide_rate
         self.spawn_mode = spawn_mode
+        self.policy, self.policy_epsilon = policy, policy_epsilon
         self.state = np.zeros(lib().oracle_state_bytes(n_envs, width, height), np.uint8)
         self.slide_params = np.zeros((n_envs, 4), np.int8)
         self.stats = np.zeros(abi.STATS_FIELDS, np.uint64)
@@ -81,7 +82,7 @@ class OracleEnv:
                               obs_dtype=self.obs_dtype, obs_enc=self.obs_enc, lut=self.lut,
                               const_plane=self.const_plane, reward_table=self.reward_table,
                               auto_reset=self.auto_reset, seed=self.seed, env_id_base=self.env_id_base,
-                              slide_mode=self.slide_mode, slide_rate=self.slide_rate, spawn_mode=self.spawn_mode,
+                              slide_mode=self.slide_mode, slide_rate=self.slide_rate, spawn_mode=self.spawn_mode, policy=self.policy, policy_epsilon=self.policy_epsilon,
                               slide_params=_p(self.slide_params), stats=_p(self.stats))
         for k, v in kw.items():
             setattr(a, k, v)

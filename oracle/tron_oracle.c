@@ -204,7 +204,24 @@ static void step_tick(const tron_step_args* a, uint64_t counter, const void* act
         float rw[2] = {0.f, 0.f}; uint8_t done = 0, winner = 0; int32_t fin = 0;
         int a1, a2;
         if (actions) { a1 = read_action(actions, a->action_dtype, 2 * (size_t)e); a2 = read_action(actions, a->action_dtype, 2 * (size_t)e + 1); }
-        else { uint32_t r[4]; philox4x32_10(a->seed, counter, env, TAG_ACTION, 0, r); a1 = (int)(r[0] >> 30); a2 = (int)(r[1] >> 30); }
+        else {
+            uint32_t r[4]; philox4x32_10(a->seed, counter, env, TAG_ACTION, 0, r); a1 = (int)(r[0] >> 30); a2 = (int)(r[1] >> 30);
+            if (a->policy == TRON_POLICY_FREE_EPS && !(m->flags & TRON_FLAG_DONE)) { /* epsilon-greedy proxy of SURVEY 8d */
+                const int64_t eps_thr = (int64_t)((double)a->policy_epsilon * 16777216.0);
+                for (int i = 0; i < 2; ++i) {
+                    int* act = i ? &a2 : &a1;
+                    *act = (int)(r[i] & 3u);
+                    if ((int64_t)(r[i] >> 8) <= eps_thr) continue;
+                    const int hr = i ? m->r2 : m->r1, hc = i ? m->c2 : m->c1;
+                    int fl[4], nf = 0;
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = hr + DR[k], cc = hc + DC[k];
+                        if (rr >= 0 && cc >= 0 && rr < W && cc < H && g[cell_index(rr, cc, H)] == TRON_TILE_EMPTY) fl[nf++] = k;
+                    }
+                    if (nf) *act = fl[mulhi32(r[2 + i], (uint32_t)nf)];
+                }
+            }
+        }
 
         if (m->flags & TRON_FLAG_DONE) { /* frozen: finished game without auto-reset */
             done = 1; winner = (uint8_t)((m->flags >> TRON_FLAG_WINNER_SHIFT) & 3u);

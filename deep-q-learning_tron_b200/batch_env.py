@@ -299,6 +299,26 @@ class BatchedTron:
                                                      self.env_id_base, out.data_ptr(), _ptr(vals), self._stream()), "tron_minimax_actions")
         return (out, vals) if want_values else out
 
+    def state_dict(self):
+        """Snapshot for checkpoint / resume (the reference only saves network weights; env state here is a few tensors)."""
+        return dict(geometry=(self.N, self.W, self.H, self.layout), state=self.state.clone(),
+                    counter=int(self.counter_dev.item()) if self.counter_dev is not None else self.counter,
+                    stats=None if self.stats is None else self.stats.clone(),
+                    slide_params=None if self.slide_params is None else self.slide_params.clone())
+
+    def load_state_dict(self, sd):
+        if tuple(sd["geometry"]) != (self.N, self.W, self.H, self.layout):
+            raise ValueError("snapshot geometry %s does not match this environment %s" % (tuple(sd["geometry"]), (self.N, self.W, self.H, self.layout)))
+        self.state.copy_(sd["state"])
+        if self.counter_dev is not None:
+            self.counter_dev.fill_(int(sd["counter"]))
+        else:
+            self.counter = int(sd["counter"])
+        if self.stats is not None and sd.get("stats") is not None:
+            self.stats.copy_(sd["stats"])
+        if self.slide_params is not None and sd.get("slide_params") is not None:
+            self.slide_params.copy_(sd["slide_params"])
+
     def stats_dict(self):
         """Summed on-device counters (episodes, wins, draws, ticks...).  Synchronises."""
         if self.stats is None:

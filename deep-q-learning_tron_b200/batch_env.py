@@ -39,6 +39,8 @@ class BatchedTron:
 
     obs layout: [N, 2, P, width+2, height+2]; obs[:, p] is player p+1's NCHW view (zero-copy).
     reward: name in abi.REWARD_POLICIES or a 5-tuple (step_base, step_per_tick, win, lose, draw).
+    layout: "tile8" (int8 grid, default), "bits10" (32-byte bit planes, 10x10 without slide modes), "trail" (trail lists, made for
+    pure ticks on large grids) or "auto" (the fastest one that fits).
     """
 
     def __init__(self, n_envs, width=10, height=10, device="cuda", obs_dtype=torch.bfloat16, obs_enc="lut1", lut=None,
@@ -47,6 +49,10 @@ class BatchedTron:
                  policy="uniform", policy_epsilon=0.0):
         _lib.require_cuda()
         self.lib = _lib.load()
+        if layout == "auto":  # fastest layout that can represent this configuration (all layouts are bit-identical through the API)
+            enc_none = (obs_enc == "none" or obs_enc == abi.ENC_NONE)
+            layout = ("bits10" if (width == 10 and height == 10 and slide_mode is None) else
+                      "trail" if (enc_none and (width + 2) * (height + 2) >= 1024) else "tile8")
         self.layout = _LAYOUT_OF[layout] if isinstance(layout, str) else int(layout)
         self.spawn_mode = {"uniform": abi.SPAWN_UNIFORM, "fair": abi.SPAWN_FAIR}[spawn_mode] if isinstance(spawn_mode, str) else int(spawn_mode)
         self.policy = {"uniform": abi.POLICY_UNIFORM, "free_eps": abi.POLICY_FREE_EPS}[policy] if isinstance(policy, str) else int(policy)

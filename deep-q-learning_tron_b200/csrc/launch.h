@@ -28,7 +28,8 @@ int launch_trail_import(void* recs, int n, int W, int H, const int8_t* tiles, co
 int launch_step_bits10(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_bits10_export(const void* planes, const void* meta, int n, int8_t* tiles, cudaStream_t s);
 int launch_bits10_import(void* planes, int n, const int8_t* tiles, cudaStream_t s);
-int tile_envs_c144();
+int tile_envs_c144(int n_envs);
+int tile_envs_small_grid(int n_envs);
 int tile_envs_generic(int cells);
 
 int launch_export_meta(const void* meta, int n, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner, int32_t* ep_len, cudaStream_t s);

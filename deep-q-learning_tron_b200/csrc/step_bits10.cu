@@ -14,7 +14,7 @@
 
 namespace tron {
 
-constexpr int kBitsThreads = 128;  // one game per thread, 128 games per CTA
+constexpr int kBitsThreads = 128;  // up to one game per thread; p.G games per CTA (128, fewer when N is small so that all SMs get work)
 constexpr int kW = 10, kHc = 12, kC = 144;
 
 struct BitCells {
@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits10_kernel(const StepPar
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int8_t* tile = (int8_t*)smem_raw;  // [128][144] Tile.value bytes, only a staging area for the encode
     const int tid = threadIdx.x;
-    const long long env0 = (long long)blockIdx.x * kBitsThreads;
-    const int nG = (int)min((long long)kBitsThreads, (long long)p.N - env0);
+    const long long env0 = (long long)blockIdx.x * p.G;
+    const int nG = (int)min((long long)p.G, (long long)p.N - env0);
     const bool owner = tid < nG;
     const long long env = env0 + tid;
     constexpr int CH = OD == TRON_F32 ? 4 : 8;
@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits10_kernel(const StepPar
 
 template <int OD, int LP, bool CP, int MODE>
 static int launch_bits_one(const StepParams& p, cudaStream_t s) {
-    const unsigned grid = (unsigned)(((long long)p.N + kBitsThreads - 1) / kBitsThreads);
-    const size_t smem = LP > 0 ? (size_t)kBitsThreads * kC : 0;
+    const unsigned grid = (unsigned)(((long long)p.N + p.G - 1) / p.G);
+    const size_t smem = LP > 0 ? (size_t)p.G * kC : 0;
     step_bits10_kernel<OD, LP, CP, MODE><<<grid, kBitsThreads, smem, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
@@ -128,7 +128,9 @@ static int launch_bits_enc(const StepParams& p, int enc_kind, cudaStream_t s) {
         default: return TRON_ERR_INVALID;
     }
 }
-int launch_step_bits10(const StepParams& p, int mode, int od, int enc_kind, cudaStream_t s) {
+int launch_step_bits10(const StepParams& p_in, int mode, int od, int enc_kind, cudaStream_t s) {
+    StepParams p = p_in;
+    p.G = tile_envs_small_grid(p.N);
     if (mode == MODE_RESET) return launch_bits_one<TRON_I8, 0, false, MODE_RESET>(p, s);
     if (mode == MODE_STEP && enc_kind == 0) return launch_bits_one<TRON_I8, 0, false, MODE_STEP>(p, s);
     if (mode == MODE_STEP) {

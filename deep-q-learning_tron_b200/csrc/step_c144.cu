@@ -2,7 +2,14 @@
 #include "step_dispatch.cuh"
 
 namespace tron {
-int tile_envs_c144() { return 128; }
+// games per CTA for the 144-cell kernels: 128 (one per thread) when there are enough games to fill the GPU, fewer for small
+// batches so that at least ~2 CTAs per SM exist (4096 games -> 16 per CTA -> 256 CTAs instead of 32)
+int tile_envs_small_grid(int n_envs) {
+    int g = n_envs / (2 * 148);
+    g -= g % 16;
+    return g < 16 ? 16 : (g > 128 ? 128 : g);
+}
+int tile_envs_c144(int n_envs) { return tile_envs_small_grid(n_envs); }
 int launch_step_c144(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s) {
     return launch_mode<144, 8>(p, mode, obs_dtype, enc_kind, s);
 }

@@ -109,22 +109,36 @@ __global__ void __launch_bounds__(kTrailThreads, 8) step_trail_kernel(const Step
     *(uint4*)rec = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
 }
 
-// ---- fused tick + observation planes on the trail-list state (large grids) -------------------------------------------
-// CTA = 128 threads, G games (G*C <= ~18 KB of shared memory).  Threads 0..G-1 tick their game on its record; then the
-// whole CTA renders the G grids into shared memory (template fill, 16-byte stores), the owners scatter their trail
-// entries and heads, and encode_tile() streams both players' planes out.  Compared with the int8 layout this skips the
-// C-byte grid read and the C-byte write-back per game-tick (8.7 KB of 26 KB at 64x64 bf16).
+// ---- fused tick + observation planes on the trail-list state ------------------------------------------------------------
+// Almost every cell of a game is template (border WALL, interior EMPTY), so no per-game grid is materialised at all:
+//   1. thread-per-game ticks the records (up to 128 games per CTA, every lane busy);
+//   2. each warp then takes its own 32 games one after the other (state broadcast with shuffles): all 32 lanes stream the
+//      TEMPLATE observation of that game -- the shared template tile in shared memory pushed through the PRMT encoder,
+//      full-sector coalesced streaming stores -- then, after __syncwarp(), overwrite the handful of trail cells and the two
+//      heads with scattered element stores that still hit L2.
+// HBM traffic per game-tick: the observation planes + one 64-byte record head; no grid read, no write-back, no
+// block-wide barrier after the template is built.
+template <int OD>
+__device__ __forceinline__ void store_elem(char* plane, int cell, const PlaneTab& t, int tile) {
+    const int sh = 8 * (tile & 7);
+    const unsigned long long lo = ((unsigned long long)t.lo1 << 32) | t.lo0, hi = ((unsigned long long)t.hi1 << 32) | t.hi0;
+    const uint32_t b = (uint32_t)((lo >> sh) & 0xFFull) | ((uint32_t)((hi >> sh) & 0xFFull) << 8);
+    if (OD == TRON_BF16) ((unsigned short*)plane)[cell] = (unsigned short)b;
+    else if (OD == TRON_F32) ((uint32_t*)plane)[cell] = b << 16;
+    else ((unsigned char*)plane)[cell] = (unsigned char)(b & 0xFFu);
+}
+
 template <int OD, int LP, bool CP, int CH, int MODE>
 __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int C = p.C, G = p.G, Hc = p.Hc, tid = threadIdx.x;
-    int8_t* tile = (int8_t*)smem_raw;                       // [G][C]
-    int8_t* tmpl = tile + ((G * C + 15) & ~15);             // [C]
+    constexpr int ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
+    const int C = p.C, G = p.G, Hc = p.Hc, tid = threadIdx.x, lane = tid & 31, P = p.P;
+    int8_t* tmpl = (int8_t*)smem_raw;  // [C] template Tile.values shared by every game of the CTA
     const long long env0 = (long long)blockIdx.x * G;
     const int nG = (int)min((long long)G, (long long)p.N - env0);
-    for (int c = tid; c < C; c += kTrailThreads) {
+    for (int c = tid; c < ((C + 3) & ~3); c += blockDim.x) {
         const int r = c / Hc, q = c - r * Hc;
-        tmpl[c] = (r == 0 || r == p.W + 1 || q == 0 || q == p.H + 1) ? (int8_t)TRON_TILE_WALL : (int8_t)TRON_TILE_EMPTY;
+        tmpl[c] = (c >= C || r == 0 || r == p.W + 1 || q == 0 || q == p.H + 1) ? (int8_t)TRON_TILE_WALL : (int8_t)TRON_TILE_EMPTY;
     }
     const bool owner = tid < nG;
     const long long env = env0 + tid;
@@ -153,33 +167,73 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
                 for (int i = 0; i < 4; ++i) if (i < g.n_fresh) g.n[g.fresh_owner[i]] += 1;
             }
         }
-        if (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1) {
-            // render: template for every game, then the owners scatter their trails and heads
-            if ((C & 15) == 0) {
-                const int per = C / 16;
-                for (int it = tid; it < nG * per; it += kTrailThreads) { const int ee = it / per; ((uint4*)(tile + ee * C))[it - ee * per] = ((const uint4*)tmpl)[it - ee * per]; }
-            } else if ((C & 3) == 0) {
+        if (!(MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1)) continue;
+        const size_t tick_off = (MODE == MODE_STEP && p.obs_every_tick) ? (size_t)t * (size_t)p.N * 2 * (size_t)P * (size_t)C * ES : 0;
+        char* obase = (char*)p.obs + tick_off;
+        __syncwarp();  // the entries appended in this tick (plain global stores of the owning lanes) are read by the whole warp below
+        const int warp_first = tid & ~31;
+        for (int src = 0; src < 32; ++src) {  // warp-uniform loop over this warp's games
+            if (warp_first + src >= nG) break;
+            const long long senv = env0 + warp_first + src;
+            const int n1 = __shfl_sync(0xFFFFFFFFu, g.n[0], src), n2 = __shfl_sync(0xFFFFFFFFu, g.n[1], src);
+            const int hr1 = __shfl_sync(0xFFFFFFFFu, e.r1, src), hc1 = __shfl_sync(0xFFFFFFFFu, e.c1, src);
+            const int hr2 = __shfl_sync(0xFFFFFFFFu, e.r2, src), hc2 = __shfl_sync(0xFFFFFFFFu, e.c2, src);
+            char* gbase = obase + (size_t)senv * 2 * P * C * ES;
+            // -- template planes
+            if constexpr (CH >= 4) {
                 const int per = C / 4;
-                for (int it = tid; it < nG * per; it += kTrailThreads) { const int ee = it / per; ((uint32_t*)(tile + ee * C))[it - ee * per] = ((const uint32_t*)tmpl)[it - ee * per]; }
-            } else {
-                for (int it = tid; it < nG * C; it += kTrailThreads) tile[it] = tmpl[it % C];
-            }
-            __syncthreads();
-            if (owner) {
-                int8_t* tl = tile + tid * C;
-                const unsigned short* ent = (const unsigned short*)(rec + 16);
-                const int nmax = max(g.n[0], g.n[1]);
-                for (int k = 0; k < nmax; ++k) {
-                    const uint32_t v = ((const uint32_t*)ent)[k];
-                    if (k < g.n[0]) { const unsigned u = v & 0xFFFFu; tl[((u & 0x7F) + 1) * Hc + (u >> 8) + 1] = (u & 0x80) ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY; }
-                    if (k < g.n[1]) { const unsigned u = v >> 16; tl[((u & 0x7F) + 1) * Hc + (u >> 8) + 1] = (u & 0x80) ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY; }
+                for (int ch = lane; ch < per; ch += 32) {
+                    const uint32_t sel = cell_selector(((const uint32_t*)tmpl)[ch]);
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                        for (int q = 0; q < LP + (CP ? 1 : 0); ++q) {
+                            uint32_t o[Enc4<OD>::WORDS];
+                            if (q < LP) Enc4<OD>::run(p.tab[pl][q < LP ? q : 0], sel, o); else Enc4<OD>::fill(p.const_plane, o);
+                            char* dst = gbase + ((size_t)(pl * P + q) * C + (size_t)ch * 4) * ES;
+                            constexpr int NW = Enc4<OD>::WORDS;
+                            if (NW == 4) st_cs((uint4*)dst, make_uint4(o[0], o[1 % NW], o[2 % NW], o[3 % NW]));
+                            else if (NW == 2) st_cs((uint2*)dst, make_uint2(o[0], o[1 % NW]));
+                            else *(uint32_t*)dst = o[0];
+                        }
                 }
-                tl[(e.r1 + 1) * Hc + e.c1 + 1] = TRON_TILE_P1_HEAD;
-                tl[(e.r2 + 1) * Hc + e.c2 + 1] = TRON_TILE_P2_HEAD;
+            } else {
+                for (int c = lane; c < C; c += 32) {
+                    const int tile = tmpl[c];
+                    for (int pl = 0; pl < 2; ++pl)
+                        for (int q = 0; q < LP + (CP ? 1 : 0); ++q) {
+                            char* plane = gbase + (size_t)(pl * P + q) * C * ES;
+                            if (q < LP) store_elem<OD>(plane, c, p.tab[pl][q < LP ? q : 0], tile);
+                            else { uint32_t o[Enc4<OD>::WORDS]; Enc4<OD>::fill(p.const_plane, o);
+                                   if (ES == 4) ((uint32_t*)plane)[c] = o[0]; else if (ES == 2) ((unsigned short*)plane)[c] = (unsigned short)o[0]; else ((unsigned char*)plane)[c] = (unsigned char)o[0]; }
+                        }
+                }
             }
-            __syncthreads();
-            encode_tile<0, kTrailThreads, OD, LP, CP, CH>(tile, nG, env0, p, (MODE == MODE_STEP && p.obs_every_tick) ? t : 0);
-            if (T > 1) __syncthreads();
+            __syncwarp();
+            // -- trail cells of both players (distinct cells), then the heads (P2 last, it wins a shared cell)
+            const uint32_t* words = (const uint32_t*)((const unsigned char*)p.grid + (size_t)senv * R + 16);
+            const int nmax = max(n1, n2);
+            for (int k = lane; k < nmax; k += 32) {
+                const uint32_t v = __ldcg(words + k);  // L2 read: another lane of this warp may have appended the entry in this tick
+#pragma unroll
+                for (int pl2 = 0; pl2 < 2; ++pl2) {
+                    if (k >= (pl2 ? n2 : n1)) continue;
+                    const unsigned u = pl2 ? (v >> 16) : (v & 0xFFFFu);
+                    const int cell = ((int)(u & 0x7F) + 1) * Hc + (int)(u >> 8) + 1;
+                    const int tile = pl2 ? ((u & 0x80) ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY) : ((u & 0x80) ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY);
+                    for (int pl = 0; pl < 2; ++pl)
+                        for (int q = 0; q < LP; ++q) store_elem<OD>(gbase + (size_t)(pl * P + q) * C * ES, cell, p.tab[pl][q], tile);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int pl = 0; pl < 2; ++pl)
+                    for (int q = 0; q < LP; ++q) {
+                        char* plane = gbase + (size_t)(pl * P + q) * C * ES;
+                        store_elem<OD>(plane, (hr1 + 1) * Hc + hc1 + 1, p.tab[pl][q], TRON_TILE_P1_HEAD);
+                        store_elem<OD>(plane, (hr2 + 1) * Hc + hc2 + 1, p.tab[pl][q], TRON_TILE_P2_HEAD);
+                    }
+            }
         }
     }
     if (MODE == MODE_STEP && owner) {
@@ -190,23 +244,15 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
 
 template <int OD, int LP, bool CP, int MODE>
 static int launch_trail_obs_one(StepParams p, cudaStream_t s) {
-    // games per CTA: ~18 KB of tile like the int8 generic kernel
-    int G = (int)(18432 / p.C);
-    G = G < 1 ? 1 : (G > kTrailThreads ? kTrailThreads : G);
+    // games per CTA: one per thread, fewer (and fewer warps) when the batch is small so that every SM gets work
+    int G = p.N / (2 * 148);
+    G -= G % 32;
+    G = G < 32 ? 32 : (G > kTrailThreads ? kTrailThreads : G);
     p.G = G;
-    const size_t smem = (size_t)((G * p.C + 15) & ~15) + (size_t)((p.C + 15) & ~15);
+    const size_t smem = (size_t)((p.C + 15) & ~15);
     const unsigned grid = (unsigned)(((long long)p.N + G - 1) / G);
-    if ((p.C & 3) == 0) {
-        auto k = step_trail_obs_kernel<OD, LP, CP, 4, MODE>;
-        static size_t lim = 48 * 1024;
-        if (smem > lim) { if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TRON_ERR_CUDA; lim = smem; }
-        k<<<grid, kTrailThreads, smem, s>>>(p);
-    } else {
-        auto k = step_trail_obs_kernel<OD, LP, CP, 1, MODE>;
-        static size_t lim = 48 * 1024;
-        if (smem > lim) { if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TRON_ERR_CUDA; lim = smem; }
-        k<<<grid, kTrailThreads, smem, s>>>(p);
-    }
+    if ((p.C & 3) == 0) step_trail_obs_kernel<OD, LP, CP, 4, MODE><<<grid, G, smem, s>>>(p);
+    else step_trail_obs_kernel<OD, LP, CP, 1, MODE><<<grid, G, smem, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 template <int OD, int MODE>

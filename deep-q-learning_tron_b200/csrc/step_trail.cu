@@ -140,8 +140,12 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
         const int r = c / Hc, q = c - r * Hc;
         tmpl[c] = (c >= C || r == 0 || r == p.W + 1 || q == 0 || q == p.H + 1) ? (int8_t)TRON_TILE_WALL : (int8_t)TRON_TILE_EMPTY;
     }
-    const bool owner = tid < nG;
-    const long long env = env0 + tid;
+    // each of the 4 warps owns gpw = G/4 consecutive games (lanes 0..gpw-1 tick them); few games per warp keep the serial
+    // per-warp streaming loop short so that the grid has many waves (32 games per warp left a 1.7-wave tail: -15 %)
+    const int gpw = G >> 2, warp = tid >> 5;
+    const int local = warp * gpw + lane;
+    const bool owner = lane < gpw && local < nG;
+    const long long env = env0 + local;
     const size_t R = trail_record_bytes(p.W, p.H);
     unsigned char* rec = (unsigned char*)p.grid + (size_t)(owner ? env : env0) * R;
     EnvState e = unpack_meta(make_uint2(0, 0));
@@ -171,10 +175,9 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
         const size_t tick_off = (MODE == MODE_STEP && p.obs_every_tick) ? (size_t)t * (size_t)p.N * 2 * (size_t)P * (size_t)C * ES : 0;
         char* obase = (char*)p.obs + tick_off;
         __syncwarp();  // the entries appended in this tick (plain global stores of the owning lanes) are read by the whole warp below
-        const int warp_first = tid & ~31;
-        for (int src = 0; src < 32; ++src) {  // warp-uniform loop over this warp's games
-            if (warp_first + src >= nG) break;
-            const long long senv = env0 + warp_first + src;
+        for (int src = 0; src < gpw; ++src) {  // warp-uniform loop over this warp's games
+            if (warp * gpw + src >= nG) break;
+            const long long senv = env0 + warp * gpw + src;
             const int n1 = __shfl_sync(0xFFFFFFFFu, g.n[0], src), n2 = __shfl_sync(0xFFFFFFFFu, g.n[1], src);
             const int hr1 = __shfl_sync(0xFFFFFFFFu, e.r1, src), hc1 = __shfl_sync(0xFFFFFFFFu, e.c1, src);
             const int hr2 = __shfl_sync(0xFFFFFFFFu, e.r2, src), hc2 = __shfl_sync(0xFFFFFFFFu, e.c2, src);
@@ -244,15 +247,15 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
 
 template <int OD, int LP, bool CP, int MODE>
 static int launch_trail_obs_one(StepParams p, cudaStream_t s) {
-    // games per CTA: one per thread, fewer (and fewer warps) when the batch is small so that every SM gets work
-    int G = p.N / (2 * 148);
-    G -= G % 32;
-    G = G < 32 ? 32 : (G > kTrailThreads ? kTrailThreads : G);
+    // games per warp: aim at >= ~6 waves of CTAs (4 CTAs/SM resident), at most one game per lane
+    int gpw = p.N / (6 * 4 * 148 * 4);
+    gpw = gpw < 1 ? 1 : (gpw > 32 ? 32 : gpw);
+    const int G = 4 * gpw;
     p.G = G;
     const size_t smem = (size_t)((p.C + 15) & ~15);
     const unsigned grid = (unsigned)(((long long)p.N + G - 1) / G);
-    if ((p.C & 3) == 0) step_trail_obs_kernel<OD, LP, CP, 4, MODE><<<grid, G, smem, s>>>(p);
-    else step_trail_obs_kernel<OD, LP, CP, 1, MODE><<<grid, G, smem, s>>>(p);
+    if ((p.C & 3) == 0) step_trail_obs_kernel<OD, LP, CP, 4, MODE><<<grid, kTrailThreads, smem, s>>>(p);
+    else step_trail_obs_kernel<OD, LP, CP, 1, MODE><<<grid, kTrailThreads, smem, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 template <int OD, int MODE>

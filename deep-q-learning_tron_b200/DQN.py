@@ -1,18 +1,43 @@
 """Drop-in for the replay side of the reference's DQN.py: Transition (DQN.py:78) and ReplayMemory (DQN.py:81-132),
 stored in the GPU replay ring (replay_push / replay_gather kernels), plus a batched restatement of the survivor
 training loop (DQN.py:135-309) on the vectorised environment."""
+import random
 from collections import namedtuple
 
+import numpy as np
 import torch
+
+from tron.player import Direction, Player
 
 import tron_b200
 from tron_b200.replay import ReplayRing
 
+device = 'cuda' if torch.cuda.is_available() else 'cpu'  # DQN.py:16
 MEM_CAPACITY = 10000  # DQN.py:32
 BATCH_SIZE = 128      # DQN.py:19
 GAMMA = 0.9           # DQN.py:20
 EPSILON_START, ESPILON_END, DECAY_RATE = 1, 0.003, 0.999  # DQN.py:23-25
 GAME_CYCLE = 20       # DQN.py:35
+
+class Ai(Player):
+    """Drop-in for DQN.Ai (DQN.py:39-75): a player that owns a Q-net and picks epsilon-greedy moves from its own 1-plane observation.
+    (In the reference's fork Game can no longer step such a player -- SURVEY section 0; the drop-in Game can.)"""
+
+    def __init__(self, epsilon=0, net=None):
+        super(Ai, self).__init__()
+        from Net.DQNNet import Net
+        self.net = net if net is not None else Net(in_planes=1).to(device)
+        self.epsilon = epsilon
+
+    def action(self, map, id):
+        game_map = map.state_for_player(id)
+        x = torch.from_numpy(np.reshape(game_map, (1, 1, game_map.shape[0], game_map.shape[1]))).float()
+        with torch.no_grad():
+            next_action = int(torch.argmax(self.net(x), 1)[0]) + 1
+        if random.random() <= self.epsilon:
+            next_action = random.randint(1, 4)
+        return Direction(next_action)
+
 
 Transition = namedtuple('Transition', ('old_state', 'action', 'new_state', 'reward', 'terminal'))
 

@@ -178,9 +178,16 @@ class Game:
             self.done = True
         return self.next_p1, self.next_p2, self.done
 
-    def main_loop(self, model, pop=None, window=None, model2=None):
+    def main_loop(self, model=None, pop=None, window=None, model2=None):
         if window:
             window.render_map(self.map())
+        if model is None:  # players that decide for themselves (DQN.Ai, MinimaxPlayer): tick until the game is over
+            while True:
+                if window:
+                    sleep(0.3)
+                if not self.next_frame(None, None, window) or self._resolve():
+                    self.done = self.done or self._finished
+                    return
         if not model2:
             model2 = model
         dev = _config.device

@@ -101,9 +101,9 @@ def _c_oracle_worker(args):
 
 def _py_port_worker(args):
     from oracle import py_port
-    seed, env_steps, W = args
+    seed, env_steps, W = args[:3]
     t0 = time.perf_counter()
-    steps, _ = py_port.play_random(seed, env_steps, W, W)
+    steps, _ = py_port.play_random(seed, env_steps, W, W, with_pop_up=len(args) > 3 and args[3])
     return steps, time.perf_counter() - t0
 
 
@@ -124,11 +124,11 @@ def cpu_c_port(W, dt, enc, budget_s, cores):
     return steps / max(r[1] for r in res), "%d procs x %d envs x %d ticks, C oracle, wall %.1fs" % (cores, n_envs, ticks, wall)
 
 
-def cpu_py_port(W, env_steps_per_core, cores):
+def cpu_py_port(W, env_steps_per_core, cores, with_pop_up=False):
     import multiprocessing as mp
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        res = pool.map(_py_port_worker, [(i, env_steps_per_core, W) for i in range(cores)])
+        res = pool.map(_py_port_worker, [(i, env_steps_per_core, W, with_pop_up) for i in range(cores)])
     steps = sum(r[0] for r in res)
     return steps / max(r[1] for r in res), steps
 
@@ -155,6 +155,7 @@ def run_reference(a):
         total += st
         dt += st / rate
     v = total / dt
+    popup_rate, _ = cpu_py_port(W, max(100, per // 4), cores, with_pop_up=True)  # BASELINE.md section 4 "variant B": + pop_up on both observations
     c_v, c_sample = cpu_c_port(W, 3, 1, min(a.cpu_seconds, 6.0), cores)
     sample = "%d host procs x %d env-steps per bench step, pure-Python port of Game.step (results and cost validated vs the live reference)" % (cores, per)
     print(json.dumps({
@@ -163,6 +164,7 @@ def run_reference(a):
         "data": "synthetic", "config": workload_config(a, None),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "cpu_c_port": {"value": c_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": c_sample},
+        "python_loop_with_pop_up": {"value": popup_rate, "unit": UNIT, "cores": cores, "note": "same loop + pop_up on both observations (DDQN data path)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))

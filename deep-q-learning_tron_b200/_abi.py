@@ -5,7 +5,7 @@ values compiled from the header with gcc.
 """
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # status
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_ALIGN = 0, -1, -2, -3, -4
@@ -19,8 +19,10 @@ ENC_NONE, ENC_LUT1, ENC_POPUP3, ENC_POPUP3_CONST = 0, 1, 2, 3
 LAYOUT_TILE8 = 0
 LAYOUT_BITS10 = 1
 LAYOUT_TRAIL = 2
+LAYOUT_BITS = 3
 OPT_SPARSE_MIN_CELLS = 1
 OPT_TILE_BYTES = 2
+OPT_ENCODE_VARIANT = 3
 SLIDE_NONE, SLIDE_TAPE, SLIDE_ICE, SLIDE_TEMPER = 0, 1, 2, 3
 SPAWN_UNIFORM, SPAWN_FAIR = 0, 1
 POLICY_UNIFORM, POLICY_FREE_EPS = 0, 1
@@ -64,6 +66,7 @@ class StepArgs(C.Structure):
         ("stats", C.c_void_p),
         ("policy", C.c_int32), ("policy_epsilon", C.c_float),
         ("n_ticks", C.c_int32), ("obs_every_tick", C.c_int32),
+        ("obs_terminal", C.c_void_p), ("extra", C.c_void_p),
     ]
 
 
@@ -72,6 +75,15 @@ class ReplayRing(C.Structure):
         ("struct_size", C.c_uint32), ("frame_elems", C.c_int32), ("frame_dtype", C.c_int32),
         ("pad0", C.c_int32), ("capacity", C.c_int64),
         ("state", C.c_void_p), ("next_state", C.c_void_p), ("action", C.c_void_p),
+        ("reward", C.c_void_p), ("done", C.c_void_p),
+    ]
+
+
+class ReplayFrames(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("frame_elems", C.c_int32), ("frame_dtype", C.c_int32),
+        ("n_slots", C.c_int32), ("rows", C.c_int64),
+        ("frames", C.c_void_p), ("terminal", C.c_void_p), ("action", C.c_void_p),
         ("reward", C.c_void_p), ("done", C.c_void_p),
     ]
 
@@ -104,9 +116,9 @@ def dtype_size(dt):
 
 
 def state_bytes(n_envs, width, height, layout=LAYOUT_TILE8):
-    per = 32 if layout == LAYOUT_BITS10 else cells_per_env(width, height)
-    if layout == LAYOUT_TRAIL:
-        per = (16 + 4 * width * height + 63) & ~63
+    per = 32 if layout == LAYOUT_BITS10 else 48 if layout == LAYOUT_BITS else cells_per_env(width, height)
+    if layout == LAYOUT_TRAIL:  # 64 hot bytes (header + 12 list words) + the cold tail of the lists
+        per = 64 + ((4 * max(0, width * height - 12) + 15) & ~15)
     grid = (n_envs * per + 255) & ~255
     meta = (8 * n_envs + 255) & ~255
     return grid + meta + 8 * n_envs
@@ -117,9 +129,11 @@ EXPORTED_SYMBOLS = (
     "tron_abi_version", "tron_status_string", "tron_device_count",
     "tron_state_bytes", "tron_state_offsets", "tron_cells_per_env", "tron_enc_planes",
     "tron_dtype_size", "tron_build_plane_tables", "tron_set_option",
-    "tron_reset", "tron_step", "tron_observe", "tron_step_many", "tron_export_grid",
+    "tron_reset", "tron_reset_ex", "tron_step", "tron_observe", "tron_step_many", "tron_export_grid",
     "tron_import_grid", "tron_random_actions", "tron_select_actions", "tron_advance_counter", "tron_minimax_actions", "tron_pop_up",
-    "replay_push", "replay_gather", "replay_sample_indices",
+    "replay_push", "replay_gather", "replay_sample_indices", "replay_sample_gather", "replay_frames_sample_gather",
     "tron_host_env_create", "tron_host_env_destroy", "tron_host_env_reset", "tron_host_env_step",
-    "tron_host_env_state", "tron_host_alloc", "tron_host_free",
+    "tron_host_env_step_begin", "tron_host_env_step_wait",
+    "tron_host_env_state", "tron_host_alloc", "tron_host_free", "tron_host_copy_bandwidth",
+    "tron_debug_violations",
 )

@@ -30,6 +30,7 @@ _SIGS = {
     "tron_dtype_size": (C.c_int, [_i]),
     "tron_build_plane_tables": (C.c_int, [_vp, _i, _vp]),
     "tron_reset": (C.c_int, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _u64, _u64, _u64, _vp]),
+    "tron_reset_ex": (C.c_int, [C.POINTER(abi.StepArgs), _vp, _vp]),
     "tron_step": (C.c_int, [C.POINTER(abi.StepArgs), _vp]),
     "tron_observe": (C.c_int, [C.POINTER(abi.StepArgs), _vp]),
     "tron_step_many": (C.c_int, [C.POINTER(abi.StepArgs), _vp]),
@@ -42,11 +43,17 @@ _SIGS = {
     "tron_pop_up": (C.c_int, [_vp, _i, _i64, _i, _vp, _i, _vp]),
     "replay_push": (C.c_int, [C.POINTER(abi.ReplayRing), _u64, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "replay_gather": (C.c_int, [C.POINTER(abi.ReplayRing), _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
-    "replay_sample_indices": (C.c_int, [_i64, _i, _u64, _u64, _vp, _vp]),
+    "replay_sample_indices": (C.c_int, [_i64, _i64, _u64, _u64, _vp, _vp]),
+    "replay_sample_gather": (C.c_int, [C.POINTER(abi.ReplayRing), _i64, _i64, _u64, _u64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "replay_frames_sample_gather": (C.c_int, [C.POINTER(abi.ReplayFrames), _i64, _i64, _i64, _u64, _u64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "tron_host_env_create": (C.c_int, [C.POINTER(_vp), C.POINTER(abi.StepArgs), _i]),
     "tron_host_env_destroy": (C.c_int, [_vp]),
     "tron_host_env_reset": (C.c_int, [_vp, _vp, _vp]),
     "tron_host_env_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tron_host_env_step_begin": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tron_host_env_step_wait": (C.c_int, [_vp]),
+    "tron_host_copy_bandwidth": (C.c_int, [C.c_size_t, _i, _i, C.POINTER(C.c_double)]),
+    "tron_debug_violations": (C.c_int, [C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "tron_host_env_state": (_vp, [_vp]),
     "tron_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "tron_host_free": (C.c_int, [_vp]),

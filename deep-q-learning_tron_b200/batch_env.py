@@ -16,7 +16,20 @@ _TORCH_OF = {abi.BF16: torch.bfloat16, abi.F32: torch.float32, abi.I8: torch.int
 _CODE_OF = {torch.bfloat16: abi.BF16, torch.float32: abi.F32, torch.int8: abi.I8, torch.uint8: abi.U8,
             torch.int32: abi.I32, torch.int64: abi.I64}
 _ENC_OF = {"none": abi.ENC_NONE, "lut1": abi.ENC_LUT1, "popup3": abi.ENC_POPUP3, "popup3_const": abi.ENC_POPUP3_CONST}
-_LAYOUT_OF = {"tile8": abi.LAYOUT_TILE8, "bits10": abi.LAYOUT_BITS10, "trail": abi.LAYOUT_TRAIL}
+_LAYOUT_OF = {"tile8": abi.LAYOUT_TILE8, "bits10": abi.LAYOUT_BITS10, "trail": abi.LAYOUT_TRAIL, "bits": abi.LAYOUT_BITS}
+
+
+def auto_layout(width, height, obs_enc, slide_mode):
+    """fastest state layout that can represent a configuration (all layouts are bit-identical through the API)"""
+    enc_none = obs_enc in ("none", abi.ENC_NONE)
+    no_slide = slide_mode in (None, abi.SLIDE_NONE)
+    if width == 10 and height == 10 and no_slide:
+        return "bits10"
+    if width * height <= 128:
+        return "bits"
+    if enc_none and (width + 2) * (height + 2) >= 1024:
+        return "trail"
+    return "tile8"
 _SLIDE_OF = {None: abi.SLIDE_NONE, "tape": abi.SLIDE_TAPE, "ice": abi.SLIDE_ICE, "temper": abi.SLIDE_TEMPER}
 
 
@@ -39,8 +52,10 @@ class BatchedTron:
 
     obs layout: [N, 2, P, width+2, height+2]; obs[:, p] is player p+1's NCHW view (zero-copy).
     reward: name in abi.REWARD_POLICIES or a 5-tuple (step_base, step_per_tick, win, lose, draw).
-    layout: "tile8" (int8 grid, default), "bits10" (32-byte bit planes, 10x10 without slide modes), "trail" (trail lists, made for
-    pure ticks on large grids) or "auto" (the fastest one that fits).
+    layout: "tile8" (int8 grid, default), "bits10" (32-byte bit planes, 10x10 without slide modes), "bits" (48-byte bit planes, any
+    board with W*H <= 128, every mode), "trail" (trail lists, made for pure ticks on large grids) or "auto" (the fastest one that fits).
+    With slide_mode="temper" the per-game [degree, weight] side features (Game.get_multy, tron/game.py:137-139) of the games the
+    latest observation shows are kept in `self.extra` ([N,2,2] f32: per player {degree, weight_p}).
     """
 
     def __init__(self, n_envs, width=10, height=10, device="cuda", obs_dtype=torch.bfloat16, obs_enc="lut1", lut=None,
@@ -49,10 +64,8 @@ class BatchedTron:
                  policy="uniform", policy_epsilon=0.0):
         _lib.require_cuda()
         self.lib = _lib.load()
-        if layout == "auto":  # fastest layout that can represent this configuration (all layouts are bit-identical through the API)
-            enc_none = (obs_enc == "none" or obs_enc == abi.ENC_NONE)
-            layout = ("bits10" if (width == 10 and height == 10 and slide_mode is None) else
-                      "trail" if (enc_none and (width + 2) * (height + 2) >= 1024) else "tile8")
+        if layout == "auto":
+            layout = auto_layout(width, height, obs_enc, slide_mode)
         self.layout = _LAYOUT_OF[layout] if isinstance(layout, str) else int(layout)
         self.spawn_mode = {"uniform": abi.SPAWN_UNIFORM, "fair": abi.SPAWN_FAIR}[spawn_mode] if isinstance(spawn_mode, str) else int(spawn_mode)
         self.policy = {"uniform": abi.POLICY_UNIFORM, "free_eps": abi.POLICY_FREE_EPS}[policy] if isinstance(policy, str) else int(policy)
@@ -83,6 +96,7 @@ class BatchedTron:
             self.stats = torch.zeros(abi.STATS_SLOTS * abi.STATS_FIELDS, dtype=torch.int64, device=self.device) if collect_stats else None
             self.slide_params = (torch.zeros((self.N, 4), dtype=torch.int8, device=self.device)
                                  if self.slide_mode == abi.SLIDE_TEMPER else None)
+            self.extra = torch.zeros((self.N, 2, 2), dtype=torch.float32, device=self.device) if self.slide_params is not None else None
 
     # ------------------------------------------------------------------ buffers
     def new_obs(self, ticks=None):
@@ -121,7 +135,7 @@ class BatchedTron:
                               reward_table=self.reward_table, auto_reset=int(self.auto_reset), seed=self.seed,
                               env_id_base=self.env_id_base, slide_mode=self.slide_mode, slide_rate=self.slide_rate, spawn_mode=self.spawn_mode,
                               policy=self.policy, policy_epsilon=self.policy_epsilon,
-                              slide_params=_ptr(self.slide_params), stats=_ptr(self.stats))
+                              slide_params=_ptr(self.slide_params), stats=_ptr(self.stats), extra=_ptr(self.extra))
         for k, v in kw.items():
             setattr(a, k, v)
         return a
@@ -147,8 +161,9 @@ class BatchedTron:
 
     # ------------------------------------------------------------------ API
     def reset(self, spawn=None, mask=None, obs=None, counter=None):
-        """Fresh games (Game.__init__).  spawn: [N,4] int8 {x1,y1,x2,y2} or None (RNG, make_game rule).
-        Returns the initial observation (or None for obs_enc='none')."""
+        """Fresh games (Game.__init__, incl. its weight/degree draws in temper mode).  spawn: [N,4] int8 {x1,y1,x2,y2} or None
+        (RNG, make_game rule).  mask: [N] uint8, reset only the flagged games.  Returns the initial observation (or None for
+        obs_enc='none')."""
         if counter is None:
             if self.counter_dev is not None:
                 counter = int(self.counter_dev.item())
@@ -157,9 +172,9 @@ class BatchedTron:
                 counter, self.counter = self.counter, self.counter + 1
         sp = self._dev(spawn, torch.int8, (self.N, 4), "spawn")
         mk = self._dev(mask, torch.uint8, (self.N,), "mask")
+        a = self._args(spawn=_ptr(sp), counter=counter, obs_enc=abi.ENC_NONE)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tron_reset(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(sp), self.spawn_mode, _ptr(mk),
-                                           self.seed, counter, self.env_id_base, self._stream()), "tron_reset")
+            _lib.check(self.lib.tron_reset_ex(C.byref(a), _ptr(mk), self._stream()), "tron_reset_ex")
         return self.observe(obs) if self.P else None
 
     def observe(self, obs=None):
@@ -174,16 +189,19 @@ class BatchedTron:
         return obs
 
     def step(self, actions=None, spawn=None, slide_tape=None, obs=None, reward=None, done=None, winner=None, ep_len=None,
-             counter=None, want_ep_len=True):
+             counter=None, want_ep_len=True, obs_terminal=None):
         """One tick of every game.  actions: [N,2] uint8/int32/int64 tensor (P1,P2) or None (uniform random policy).
-        Output tensors may be passed in to avoid allocation.  -> StepResult(obs, reward, done, winner, ep_len)"""
+        Output tensors may be passed in to avoid allocation.  obs_terminal: tensor like obs; the rows of games that finished in this
+        tick (and were auto-reset) receive the finished game's last frame (DDQN.py:270-308 next_state), other rows are untouched.
+        -> StepResult(obs, reward, done, winner, ep_len)"""
         counter, cdev, adv = self._take_counter(counter)
         N, dev = self.N, self.device
         if actions is not None:
             if not torch.is_tensor(actions):
                 actions = torch.as_tensor(actions)
             if actions.device != dev or not actions.is_contiguous() or actions.dtype not in (torch.uint8, torch.int32, torch.int64):
-                actions = actions.to(device=dev, dtype=torch.uint8 if actions.dtype not in (torch.int32, torch.int64) else actions.dtype).contiguous()
+                # other dtypes go through int64 so that out-of-range values stay out of range (and are counted as bad actions)
+                actions = actions.to(device=dev, dtype=actions.dtype if actions.dtype in (torch.uint8, torch.int32, torch.int64) else torch.int64).contiguous()
             if tuple(actions.shape) != (N, 2):
                 raise ValueError("actions must have shape (%d, 2), got %s" % (N, tuple(actions.shape)))
         sp = self._dev(spawn, torch.int8, (N, 4), "spawn")
@@ -193,6 +211,8 @@ class BatchedTron:
         self._out(obs, (N, 2, self.P, self.W + 2, self.H + 2), _TORCH_OF.get(self.obs_dtype), "obs") if self.P else None
         self._out(reward, (N, 2), torch.float32, "reward"); self._out(done, (N,), torch.uint8, "done")
         self._out(winner, (N,), torch.uint8, "winner"); self._out(ep_len, (N,), torch.int32, "ep_len")
+        if obs_terminal is not None:
+            self._out(obs_terminal, (N, 2, self.P, self.W + 2, self.H + 2), _TORCH_OF.get(self.obs_dtype), "obs_terminal")
         if obs is None and self.P:
             obs = self.new_obs()
         if reward is None:
@@ -205,7 +225,7 @@ class BatchedTron:
             ep_len = torch.empty(N, dtype=torch.int32, device=dev)
         a = self._args(actions=_ptr(actions), action_dtype=0 if actions is None else _CODE_OF[actions.dtype], obs=_ptr(obs),
                        reward=reward.data_ptr(), done=done.data_ptr(), winner=winner.data_ptr(), ep_len_out=_ptr(ep_len),
-                       spawn=_ptr(sp), slide_tape=_ptr(sl), counter=counter, counter_dev=cdev)
+                       spawn=_ptr(sp), slide_tape=_ptr(sl), counter=counter, counter_dev=cdev, obs_terminal=_ptr(obs_terminal))
         with torch.cuda.device(dev):
             _lib.check(self.lib.tron_step(C.byref(a), self._stream()), "tron_step")
             self._advance(adv)
@@ -218,7 +238,7 @@ class BatchedTron:
         act = None
         if actions is not None:
             act = actions if torch.is_tensor(actions) else torch.as_tensor(actions)
-            dt = act.dtype if act.dtype in (torch.int32, torch.int64) else torch.uint8
+            dt = act.dtype if act.dtype in (torch.uint8, torch.int32, torch.int64) else torch.int64
             act = act.to(device=dev, dtype=dt).contiguous()
             if tuple(act.shape) != (T, N, 2):
                 raise ValueError("actions must have shape (%d, %d, 2), got %s" % (T, N, tuple(act.shape)))
@@ -335,16 +355,25 @@ class BatchedTron:
 
 
 class HostTron:
-    """Host-buffer front end (tron_host_env_*): numpy in, numpy out, copies overlapped with the kernels."""
+    """Host-buffer front end (tron_host_env_*): numpy in, numpy out.  Observations default to int8 (the reference's Game.step
+    returns integer arrays, tron/map.py:83-84); bf16 / f32 are available for callers that feed a net directly.
 
-    def __init__(self, n_envs, width=10, height=10, obs_dtype=abi.BF16, obs_enc=abi.ENC_LUT1, lut=None, const_plane=0.0,
-                 reward="ddqn", auto_reset=True, seed=0, env_id_base=0, n_chunks=8, layout="tile8"):
+    step() blocks until the outputs have landed.  step_begin() / step_wait() pipeline consecutive steps (two in flight at most):
+    the outputs of step t land in the buffer set t % 2 (self.obs2[t % 2] ...), and the tick kernels of step t+1 run while step t
+    is still draining over PCIe."""
+
+    def __init__(self, n_envs, width=10, height=10, obs_dtype=abi.I8, obs_enc=abi.ENC_LUT1, lut=None, const_plane=0.0,
+                 reward="ddqn", auto_reset=True, seed=0, env_id_base=0, n_chunks=8, layout="auto", double_buffer=False):
         import numpy as np
         _lib.require_cuda()
         self.np = np
         self.lib = _lib.load()
         self.N, self.W, self.H = n_envs, width, height
         self.P, self.obs_dtype = abi.enc_planes(obs_enc), obs_dtype
+        if layout == "auto":
+            layout = auto_layout(width, height, obs_enc, None)
+            if layout == "trail":
+                layout = "tile8"
         proto = abi.new_step_args(n_envs=n_envs, width=width, height=height, obs_dtype=obs_dtype, obs_enc=obs_enc,
                                   layout=_LAYOUT_OF[layout] if isinstance(layout, str) else int(layout),
                                   lut=tuple(lut) if lut is not None else (0,) * 6, const_plane=const_plane,
@@ -354,13 +383,17 @@ class HostTron:
         _lib.check(self.lib.tron_host_env_create(C.byref(self.handle), C.byref(proto), n_chunks), "tron_host_env_create")
         self._pinned = []
         npdt = {abi.BF16: np.uint16, abi.F32: np.float32, abi.I8: np.int8}[obs_dtype]
-        self.obs = self.pinned((n_envs, 2, self.P, width + 2, height + 2), npdt) if self.P else None
-        self.actions = self.pinned((n_envs, 2), np.uint8)
-        self.reward = self.pinned((n_envs, 2), np.float32)
-        self.done = self.pinned((n_envs,), np.uint8)
-        self.winner = self.pinned((n_envs,), np.uint8)
+        nb = 2 if double_buffer else 1
+        self.obs2 = [self.pinned((n_envs, 2, self.P, width + 2, height + 2), npdt) if self.P else None for _ in range(nb)]
+        self.actions2 = [self.pinned((n_envs, 2), np.uint8) for _ in range(nb)]
+        self.reward2 = [self.pinned((n_envs, 2), np.float32) for _ in range(nb)]
+        self.done2 = [self.pinned((n_envs,), np.uint8) for _ in range(nb)]
+        self.winner2 = [self.pinned((n_envs,), np.uint8) for _ in range(nb)]
+        self.obs, self.actions, self.reward, self.done, self.winner = self.obs2[0], self.actions2[0], self.reward2[0], self.done2[0], self.winner2[0]
+        self._begun = self._waited = 0
 
     def pinned(self, shape, dtype):
+        """pinned host array, pages on the NUMA node of the current CUDA device (tron_host_alloc)"""
         np = self.np
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         p = C.c_void_p()
@@ -373,16 +406,35 @@ class HostTron:
         sp = None if spawn is None else self.np.ascontiguousarray(spawn, self.np.int8)
         _lib.check(self.lib.tron_host_env_reset(self.handle, None if sp is None else sp.ctypes.data, None if self.obs is None else self.obs.ctypes.data),
                    "tron_host_env_reset")
+        self._begun = self._waited = 0
         return self.obs
 
-    def step(self, actions=None, spawn=None):
+    def _call(self, fn, name, b, actions, spawn):
         if actions is not None:
-            self.actions[...] = actions
+            self.actions2[b][...] = actions
         sp = None if spawn is None else self.np.ascontiguousarray(spawn, self.np.int8)
-        _lib.check(self.lib.tron_host_env_step(self.handle, self.actions.ctypes.data, None if sp is None else sp.ctypes.data,
-                                               None if self.obs is None else self.obs.ctypes.data, self.reward.ctypes.data,
-                                               self.done.ctypes.data, self.winner.ctypes.data), "tron_host_env_step")
+        self._spawn_keepalive = sp
+        _lib.check(fn(self.handle, self.actions2[b].ctypes.data, None if sp is None else sp.ctypes.data,
+                      None if self.obs2[b] is None else self.obs2[b].ctypes.data, self.reward2[b].ctypes.data,
+                      self.done2[b].ctypes.data, self.winner2[b].ctypes.data), name)
+
+    def step(self, actions=None, spawn=None):
+        self._call(self.lib.tron_host_env_step, "tron_host_env_step", 0, actions, spawn)
         return self.obs, self.reward, self.done, self.winner
+
+    def step_begin(self, actions=None, spawn=None):
+        """enqueue one step and return; its outputs belong to the library until the matching step_wait()"""
+        b = self._begun % len(self.obs2)
+        self._call(self.lib.tron_host_env_step_begin, "tron_host_env_step_begin", b, actions, spawn)
+        self._begun += 1
+        return b
+
+    def step_wait(self):
+        """block until the oldest outstanding step has landed -> (obs, reward, done, winner) of that step"""
+        _lib.check(self.lib.tron_host_env_step_wait(self.handle), "tron_host_env_step_wait")
+        b = self._waited % len(self.obs2)
+        self._waited += 1
+        return self.obs2[b], self.reward2[b], self.done2[b], self.winner2[b]
 
     def state_ptr(self):
         return self.lib.tron_host_env_state(self.handle)
@@ -392,6 +444,7 @@ class HostTron:
             self.lib.tron_host_env_destroy(self.handle)
             self.handle = None
         self.obs = self.actions = self.reward = self.done = self.winner = None
+        self.obs2 = self.actions2 = self.reward2 = self.done2 = self.winner2 = []
         for p in self._pinned:
             self.lib.tron_host_free(p)
         self._pinned = []
@@ -401,6 +454,13 @@ class HostTron:
             self.close()
         except Exception:
             pass
+
+
+def host_copy_bandwidth(nbytes=1 << 30, direction="d2h", repeats=3):
+    """measured PCIe ceiling of the current device: GB/s of back-to-back cudaMemcpyAsync between NUMA-local pinned memory and HBM"""
+    out = C.c_double()
+    _lib.check(_lib.load().tron_host_copy_bandwidth(int(nbytes), 0 if direction == "h2d" else 1, int(repeats), C.byref(out)), "tron_host_copy_bandwidth")
+    return out.value
 
 
 class GraphedStep:

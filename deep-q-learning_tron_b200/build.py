@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libtron_b200.so")
-SOURCES = ["abi.cu", "step_c144.cu", "step_generic.cu", "step_sparse.cu", "step_bits10.cu", "step_trail.cu", "minimax.cu", "misc_kernels.cu"]
+LIB_DEBUG = os.path.join(HERE, "libtron_b200_debug.so")  # -DTRON_DEBUG: device-side range checks, tests only
+SOURCES = ["abi.cu", "host_env.cu", "step_c144.cu", "step_generic.cu", "step_sparse.cu", "step_bits.cu", "step_trail.cu", "minimax.cu", "misc_kernels.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-Xptxas", "-v"]
 
@@ -30,14 +31,18 @@ def _stale(target, srcs):
     return any(os.path.getmtime(s) > t for s in srcs)
 
 
-def build(force=False, verbose=False):
-    os.makedirs(OBJ, exist_ok=True)
+def build(force=False, verbose=False, debug=False):
+    """debug=True builds libtron_b200_debug.so (every computed index range-checked on the device) next to the release library."""
+    obj_dir = OBJ + ("_debug" if debug else "")
+    lib = LIB_DEBUG if debug else LIB
+    os.makedirs(obj_dir, exist_ok=True)
     deps = _deps()
+    flags = NVCC_FLAGS + (["-DTRON_DEBUG"] if debug else [])
 
     def compile_one(src):
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
         if force or _stale(obj, [os.path.join(CSRC, src)] + deps):
-            cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+            cmd = [_nvcc()] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
             r = subprocess.run(cmd, capture_output=True, text=True)
             with open(obj + ".log", "w") as f:
                 f.write(r.stdout + r.stderr)
@@ -49,13 +54,13 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    if force or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    if force or _stale(lib, objs):
+        cmd = [_nvcc(), "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr[-4000:])
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

@@ -9,6 +9,37 @@
 namespace tron {
 
 // ---------------------------------------------------------------------------------------------
+// Debug build (-DTRON_DEBUG, libtron_b200_debug.so, tests only): every computed cell index, trail-list position, ring slot
+// and env ownership is range-checked; a violation is counted (first code kept) and the access is skipped, so a test can
+// assert "no violations" instead of relying on compute-sanitizer.  Release builds compile the checks away.
+// ---------------------------------------------------------------------------------------------
+enum : int {
+    DBG_CELL_INDEX = 1,   // cell index outside [0, C)
+    DBG_TRAIL_COUNT = 2,  // trail-list position >= W*H
+    DBG_RING_SLOT = 3,    // replay ring slot outside [0, capacity)
+    DBG_ENV_OWNER = 4,    // a thread touched an env outside [0, N)
+    DBG_HEAD_RANGE = 5,   // head coordinate outside [-1, W] x [-1, H]
+    DBG_BIT_INDEX = 6     // bit-plane index outside [0, 128)
+};
+#ifdef TRON_DEBUG
+// one counter pair per translation unit (no relocatable device code needed); each unit registers a reader with the library
+static __device__ unsigned long long g_dbg_count = 0ull;
+static __device__ int g_dbg_first = 0;
+__device__ __forceinline__ bool dbg_fail(int code) {
+    if (atomicAdd(&g_dbg_count, 1ull) == 0ull) g_dbg_first = code;
+    return false;
+}
+int dbg_register(int (*reader)(unsigned long long*, int*));  // misc_kernels.cu
+static int dbg_read_unit(unsigned long long* c, int* f) {
+    return (cudaMemcpyFromSymbol(c, g_dbg_count, sizeof *c) == cudaSuccess && cudaMemcpyFromSymbol(f, g_dbg_first, sizeof *f) == cudaSuccess) ? 0 : -1;
+}
+static const int g_dbg_registered = dbg_register(dbg_read_unit);
+#define TRON_DCHECK(cond, code) ((cond) ? true : ::tron::dbg_fail(code))
+#else
+#define TRON_DCHECK(cond, code) (true)
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG.  Counter = {tick counter (64b), stream id (48b) | tag | sub},
 // key = seed.  One stream per global env id, so results do not depend on how envs are sharded.
 // ---------------------------------------------------------------------------------------------

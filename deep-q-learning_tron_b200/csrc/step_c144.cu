@@ -5,7 +5,7 @@ namespace tron {
 // games per CTA for the 144-cell kernels: 128 (one per thread) when there are enough games to fill the GPU, fewer for small
 // batches so that at least ~2 CTAs per SM exist (4096 games -> 16 per CTA -> 256 CTAs instead of 32)
 int tile_envs_small_grid(int n_envs) {
-    int g = n_envs / (2 * 148);
+    int g = n_envs / (2 * sm_count());
     g -= g % 16;
     return g < 16 ? 16 : (g > 128 ? 128 : g);
 }

@@ -15,11 +15,7 @@ template <int C_T, int OD, int LP, bool CP, int CH, int MODE>
 int launch_one(const StepParams& p, cudaStream_t s) {
     auto kern = step_tile_kernel<C_T, kThreads, OD, LP, CP, CH, MODE>;
     const size_t smem = tile_smem_bytes(p.G, p.C);
-    static size_t smem_limit = 48 * 1024;  // raised lazily; per instantiation
-    if (smem > smem_limit) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return TRON_ERR_CUDA;
-        smem_limit = smem;
-    }
+    if (smem > 48 * 1024 && ensure_dynamic_smem((const void*)kern, smem) != TRON_OK) return TRON_ERR_CUDA;
     const unsigned grid = (unsigned)(((long long)p.N + p.G - 1) / p.G);
     kern<<<grid, kThreads, smem, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;

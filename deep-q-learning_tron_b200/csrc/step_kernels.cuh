@@ -60,14 +60,16 @@ __device__ __forceinline__ int elem_size() { return OD == TRON_F32 ? 4 : OD == T
 
 // Encode both players' observation planes of a tile of nG games held in shared memory as int8 Tile.values.
 // Every warp-wide store covers whole 32-byte sectors; values come from 8-entry byte tables via PRMT (common.cuh).
+// `only` != nullptr: encode just the games whose flag is set (terminal frames of finished games -> obs_terminal).
 template <int C_T, int NT, int OD, int LP, bool CP, int CH>
-__device__ __forceinline__ void encode_tile(const int8_t* tile, int nG, long long env0, const StepParams& p, int t) {
+__device__ __forceinline__ void encode_tile(const int8_t* tile, int nG, long long env0, const StepParams& p, int t, void* out = nullptr,
+                                            const uint8_t* only = nullptr) {
     const int C = C_T ? C_T : p.C;
     const int tid = threadIdx.x;
             constexpr int ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
             const int P = p.P;
             const size_t tick_off = (size_t)t * (size_t)p.N * 2 * (size_t)P * (size_t)C * ES;
-            char* obase = (char*)p.obs + tick_off;
+            char* obase = (char*)(out ? out : p.obs) + tick_off;
             if constexpr (CH >= 4) {
                 const int per = C / CH;
                 // one item = CH consecutive cells of one game -> one store per (player, plane)
@@ -97,17 +99,21 @@ __device__ __forceinline__ void encode_tile(const int8_t* tile, int nG, long lon
                     }
                 };
                 if (C_T == 0 && per >= 4 * NT) {  // large grids: game-major loops, no per-item division
-                    for (int e = 0; e < nG; ++e)
+                    for (int e = 0; e < nG; ++e) {
+                        if (only && !only[e]) continue;
                         for (int ch = tid; ch < per; ch += NT) emit(e, ch);
+                    }
                 } else {
                     for (int it = tid; it < nG * per; it += NT) {
                         const int e = it / per;
+                        if (only && !only[e]) continue;
                         emit(e, it - e * per);
                     }
                 }
             } else {  // scalar fallback for odd cell counts
                 for (int it = tid; it < nG * C; it += NT) {
                     const int e = it / C, c = it - e * C;
+                    if (only && !only[e]) continue;
                     const uint32_t sel = (uint32_t)tile[it] & 7u;
                     for (int pl = 0; pl < 2; ++pl)
                         for (int q = 0; q < LP + (CP ? 1 : 0); ++q) {
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
                 BoxRegs bx;
                 bool do_reset;
                 if (C_T == 0 && sparse_wb) {  // large grids: remember the <=6 bytes this tick changes, write only those back
-                    LoggedByteCells cells{tile + tid * C, p.Hc, 0, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+                    LoggedByteCells cells{tile + tid * C, p.Hc, C, 0, {0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
                     do_reset = env_tick<MODE, false>(cells, p, e, env, t, tid, bx);
                     if (!do_reset) {
                         int8_t* gg = p.grid + (size_t)env * C;
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
                         for (int k = 0; k < 6; ++k) if (k < cells.n) gg[cells.idx[k]] = cells.val[k];
                     }
                 } else {
-                    ByteCells cells{tile + tid * C, p.Hc};
+                    ByteCells cells{tile + tid * C, p.Hc, C};
                     do_reset = env_tick<MODE, false>(cells, p, e, env, t, tid, bx);
                 }
                 if (MODE == MODE_RESET && do_reset && p.boxes) {  // a fresh grid has exactly two non-template cells
@@ -205,6 +211,10 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
                 rflag[tid] = do_reset ? 1 : 0;
             }
             __syncthreads();
+            if (LP > 0 && MODE == MODE_STEP && p.obs_term) {  // last frame of the games that just finished, before they are rebuilt
+                encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, p.obs_every_tick ? t : 0, p.obs_term, rflag);
+                __syncthreads();
+            }
             // ------------------------------------------------------------ phase 2: rebuild reset games
             {
                 constexpr int V = (C_T != 0 && C_T % 16 == 0) ? 16 : 4;  // template copy granularity (C % 4 == 0 or scalar)
@@ -267,6 +277,7 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
             }
         }
         // ---------------------------------------------------------------- phase 3: observation planes
+        if (MODE == MODE_OBSERVE && owner) emit_extra(p, env);
         if (LP > 0 && (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1))
             encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, (MODE == MODE_STEP && p.obs_every_tick) ? t : 0);
         if (T > 1) __syncthreads();  // next tick's phase 1 rewrites the tile

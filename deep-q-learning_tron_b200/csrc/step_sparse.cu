@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kSparseThreads) step_sparse_kernel(const StepP
     }
     int8_t* g = p.grid + (size_t)(valid ? env : 0) * C;
     for (int t = 0; t < p.T; ++t) {
-        ByteCells cells{g, Hc};
+        ByteCells cells{g, Hc, C};
         const bool do_reset = valid ? env_tick<MODE_STEP, true>(cells, p, e, env, t, tid, bx) : false;
         unsigned mask = __ballot_sync(0xFFFFFFFFu, do_reset);
         const uint2 pb = pack_boxes(bx);

@@ -1,36 +1,61 @@
-// step_trail.cu -- pure tick for LARGE grids on a TRAIL-LIST state (TRON_LAYOUT_TRAIL).
+// step_trail.cu -- ticks for LARGE grids on a TRAIL-LIST state (TRON_LAYOUT_TRAIL).
 //
-// A dense 64x64 grid is 4,356 B per game of which a tick touches ~6 cells scattered over several DRAM rows; the int8
-// sparse kernel is therefore bound by random 32-byte DRAM operations (~15 per game-tick), not by bandwidth.  Here a game
-// is ONE record whose hot part is contiguous:
-//     [0:8)   tron_meta (heads, alive/done/winner flags, ep_len)      [8:10) n1   [10:12) n2   [12:16) reserved
-//     [16: )  trail cells, interleaved by player: entry (k, player) at 16 + 2*(2k + player), 2 bytes = {p0 | slide<<7, p1}
-// Every tile a player leaves behind (body, or slide tile in ice/temper mode) is appended to its list; walls are implicit
-// and heads live in the meta.  "Is this cell free?" is a scan of both lists -- a handful of entries for typical episodes --
-// and a reset is n1 = n2 = 0.  The first 12 ticks of both players sit in the record's first 64 bytes, so a game-tick is
-// normally one 64-byte read and one or two sector writes.  Capacity is W*H entries per player (trail cells are distinct
-// interior cells), so the representation is exact for any episode; tron_export_grid renders the Tile.value grid.
-// Observations are not produced from this layout (use TRON_LAYOUT_TILE8 / BITS10 for the fused obs path).
+// A dense 64x64 grid is 4,356 B per game of which a tick touches ~6 cells scattered over several DRAM rows; the int8 sparse
+// kernel is therefore bound by random 32-byte DRAM operations (~15 per game-tick), not by bandwidth.  Here a game is
+//     header  16 B : tron_meta (heads, alive/done/winner flags, ep_len) | n1 u16 | n2 u16 | 4 B reserved
+//     list         : the trail cells both players left behind, interleaved by player: word k = {entry (k, P1), entry (k, P2)},
+//                    an entry = 2 bytes {p0 | slide<<7, p1}; capacity W*H entries per player (trail cells are distinct
+//                    interior cells), so the representation is exact for any episode.
+// Walls are implicit and heads live in the header.  "Is this cell free?" is a scan of both lists -- a handful of entries for
+// typical episodes -- and a reset is n1 = n2 = 0.
+//
+// Memory layout (round 2): the header and list words 0..11 of EVERY game -- 64 "hot" bytes -- are four dense uint4 arrays
+// hot[q][state_N] (q = 0 header, q = 1..3 list words 4(q-1)..4(q-1)+3); list words >= 12 live in a per-game cold area behind
+// them.  A tick of thread-per-game is then four fully coalesced 512-byte warp loads, one coalesced header store and one
+// coalesced store of the uint4 that received this tick's entries: the kernel streams at HBM bandwidth instead of paying one
+// DRAM row activation per game (round 1 kept a game's record contiguous, 16 KB apart from its neighbours: 0.34 of peak).
+// Only episodes longer than 12 ticks touch the cold area.
 #include "launch.h"
 #include "step_kernels.cuh"
 
 namespace tron {
 
 constexpr int kTrailThreads = 128;
-constexpr int kTrailHot = 24;  // entries held in registers (bytes 16..64 of the record)
+constexpr int kTrailHot = 12;  // list words held in the hot arrays / in registers (entries 0..11 of both players)
 
-// a multiple of 64 bytes: the hot head of a record (header + first 24 entries) is then exactly one 64-byte DRAM atom /
-// two L2 sectors, and the kernel may always load the first 64 bytes
-__host__ __device__ inline size_t trail_record_bytes(int W, int H) { return (16u + 4u * (size_t)W * (size_t)H + 63u) & ~(size_t)63u; }
-size_t trail_record_bytes_host(int W, int H) { return trail_record_bytes(W, H); }
+__host__ __device__ inline int trail_cold_words(int W, int H) {
+    const int n = W * H - kTrailHot;
+    return n <= 0 ? 0 : ((n + 3) & ~3);
+}
+size_t trail_game_bytes_host(int W, int H) { return 64u + 4u * (size_t)trail_cold_words(W, H); }
+
+// address of list word k of the game at dense index i
+struct TrailStore {
+    uint4* hot;
+    uint32_t* cold;
+    long long SN;  // games in the arrays
+    int cw;        // cold words per game
+    __device__ __forceinline__ uint32_t* word(long long i, int k) const {
+        return k < kTrailHot ? ((uint32_t*)(hot + (long long)(1 + (k >> 2)) * SN + i) + (k & 3)) : (cold + i * cw + (k - kTrailHot));
+    }
+};
+__host__ __device__ inline TrailStore trail_store(const StepParams& p) {
+    TrailStore s;
+    s.hot = (uint4*)p.grid;
+    s.SN = p.state_N;
+    s.cw = trail_cold_words(p.W, p.H);
+    s.cold = (uint32_t*)((char*)p.grid + 64ull * (unsigned long long)p.state_N);
+    return s;
+}
 
 struct TrailCells {
-    unsigned char* rec;       // this game's record in HBM
-    int n[2];                 // entries per player at the start of the tick (those are in hot[] / HBM)
-    uint32_t hot[kTrailHot / 2];  // first 24 entries as loaded
+    uint32_t hot[kTrailHot];  // list words 0..11
+    uint32_t* cold;           // this game's cold words (list words 12..)
+    int n[2];                 // entries per player at the start of the tick (those are in hot[] / cold[])
     unsigned short fresh[4];  // entries appended during this tick (two bodies, up to two slide tiles)
     int fresh_owner[4], n_fresh;
     int W, H;
+    unsigned dirty;           // bit q: hot uint4 q changed
 
     __device__ __forceinline__ static unsigned short pack(int r, int c, bool slide) { return (unsigned short)((r & 0x7F) | (slide ? 0x80 : 0) | (c << 8)); }
 
@@ -39,17 +64,14 @@ struct TrailCells {
         const unsigned key = (unsigned)(r & 0x7F) | ((unsigned)c << 8);
         bool hit = false;
 #pragma unroll
-        for (int w = 0; w < kTrailHot / 2; ++w) {  // word w = {entry (k=w, P1), entry (k=w, P2)}
+        for (int w = 0; w < kTrailHot; ++w) {  // word w = {entry (k=w, P1), entry (k=w, P2)}
             const unsigned e1 = hot[w] & 0xFF7Fu, e2 = (hot[w] >> 16) & 0xFF7Fu;
             hit |= (w < n[0] && e1 == key) | (w < n[1] && e2 == key);
         }
         const int nmax = max(n[0], n[1]);
-        if (nmax > kTrailHot / 2) {  // long episode: the rest of the lists, straight from memory
-            const uint32_t* words = (const uint32_t*)(rec + 16);
-            for (int w = kTrailHot / 2; w < nmax; ++w) {
-                const uint32_t v = words[w];
-                hit |= (w < n[0] && (v & 0xFF7Fu) == key) | (w < n[1] && ((v >> 16) & 0xFF7Fu) == key);
-            }
+        for (int w = kTrailHot; w < nmax; ++w) {  // long episode: the rest of the lists, straight from memory
+            const uint32_t v = cold[w - kTrailHot];
+            hit |= (w < n[0] && (v & 0xFF7Fu) == key) | (w < n[1] && ((v >> 16) & 0xFF7Fu) == key);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) hit |= (i < n_fresh && (fresh[i] & 0xFF7Fu) == key);
@@ -64,15 +86,46 @@ struct TrailCells {
         else if (tile == TRON_TILE_P2_SLIDE) { owner = 1; slide = true; }
         else return;  // heads are metadata
         if (r < 0 || c < 0 || r >= W || c >= H) return;  // a head that left the board leaves no trail tile there
-        int cnt = n[owner];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) cnt += (i < n_fresh && fresh_owner[i] == owner);
         const unsigned short e = pack(r, c, slide);
-        ((unsigned short*)(rec + 16))[2 * cnt + owner] = e;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             if (i == n_fresh) { fresh[i] = e; fresh_owner[i] = owner; }
         n_fresh = min(n_fresh + 1, 4);
+    }
+    // append this tick's entries to the lists (registers for list words < 12, memory beyond)
+    __device__ __forceinline__ void commit() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i >= n_fresh) continue;
+            const int o = fresh_owner[i], k = n[o];
+            if (!TRON_DCHECK(k < W * H, DBG_TRAIL_COUNT)) continue;
+            const uint32_t v = (uint32_t)fresh[i] << (16 * o), keep = o ? 0x0000FFFFu : 0xFFFF0000u;
+            if (k < kTrailHot) {
+#pragma unroll
+                for (int w = 0; w < kTrailHot; ++w)
+                    if (w == k) hot[w] = (hot[w] & keep) | v;
+                dirty |= 1u << (1 + (k >> 2));
+            } else {
+                ((unsigned short*)(cold + (k - kTrailHot)))[o] = fresh[i];
+            }
+            n[o] = k + 1;
+        }
+        n_fresh = 0;
+    }
+    __device__ __forceinline__ void load_hot(const TrailStore& st, long long i, int upto_words) {
+        // upto_words: list words that can hold valid entries (lazy variant) or kTrailHot
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (4 * q < upto_words) v = st.hot[(long long)(1 + q) * st.SN + i];
+            hot[4 * q] = v.x; hot[4 * q + 1] = v.y; hot[4 * q + 2] = v.z; hot[4 * q + 3] = v.w;
+        }
+    }
+    __device__ __forceinline__ void store_dirty(const TrailStore& st, long long i) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (dirty & (1u << (1 + q))) st.hot[(long long)(1 + q) * st.SN + i] = make_uint4(hot[4 * q], hot[4 * q + 1], hot[4 * q + 2], hot[4 * q + 3]);
+        dirty = 0;
     }
 };
 
@@ -81,32 +134,29 @@ __global__ void __launch_bounds__(kTrailThreads, 8) step_trail_kernel(const Step
     const int tid = threadIdx.x;
     const long long env = (long long)blockIdx.x * kTrailThreads + tid;
     if (env >= p.N) return;
-    const size_t R = trail_record_bytes(p.W, p.H);
-    unsigned char* rec = (unsigned char*)p.grid + (size_t)env * R;
-    uint4 hdr = *(const uint4*)rec;
+    const TrailStore st = trail_store(p);
+    const long long i = p.state_off + env;
+    const uint4 hdr = st.hot[i];
     EnvState e = unpack_meta(make_uint2(hdr.x, hdr.y));
     TrailCells g;
-    g.rec = rec; g.W = p.W; g.H = p.H;
+    g.W = p.W; g.H = p.H; g.cold = st.cold + i * st.cw; g.dirty = 0; g.n_fresh = 0;
     g.n[0] = (int)(hdr.z & 0xFFFFu); g.n[1] = (int)(hdr.z >> 16);
+    if (MODE == MODE_STEP) {
+        // lazy variant: a list word beyond max(n1,n2) holds nothing valid, and this tick appends at most two entries per player,
+        // so only the uint4s up to word max(n)+1 are needed (second round trip only for games older than 2 ticks)
+        const int need = (p.variant & 4) ? min(kTrailHot, max(g.n[0], g.n[1]) + 2 * p.T) : kTrailHot;
+        g.load_hot(st, i, need);
+    }
     const int T = MODE == MODE_STEP ? p.T : 1;
     for (int t = 0; t < T; ++t) {
-        if (MODE == MODE_STEP) {
-            const uint4 a = *(const uint4*)(rec + 16), b = *(const uint4*)(rec + 32), c = *(const uint4*)(rec + 48);
-            g.hot[0] = a.x; g.hot[1] = a.y; g.hot[2] = a.z; g.hot[3] = a.w; g.hot[4] = b.x; g.hot[5] = b.y; g.hot[6] = b.z; g.hot[7] = b.w;
-            g.hot[8] = c.x; g.hot[9] = c.y; g.hot[10] = c.z; g.hot[11] = c.w;
-        }
-        g.n_fresh = 0;
         BoxRegs bx;
         const bool do_reset = env_tick<MODE, false>(g, p, e, env, t, tid, bx);
-        if (do_reset) { g.n[0] = g.n[1] = 0; }
-        else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) if (i < g.n_fresh) g.n[g.fresh_owner[i]] += 1;
-        }
-        if (T > 1) __threadfence_block();  // this thread re-reads its own appended entries on the next tick
+        if (do_reset) { g.n[0] = g.n[1] = 0; g.n_fresh = 0; }
+        else g.commit();
     }
     const uint2 m = pack_meta(e);
-    *(uint4*)rec = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
+    st.hot[i] = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
+    if (MODE == MODE_STEP) g.store_dirty(st, i);
 }
 
 // ---- fused tick + observation planes on the trail-list state ------------------------------------------------------------
@@ -146,32 +196,28 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
     const int local = warp * gpw + lane;
     const bool owner = lane < gpw && local < nG;
     const long long env = env0 + local;
-    const size_t R = trail_record_bytes(p.W, p.H);
-    unsigned char* rec = (unsigned char*)p.grid + (size_t)(owner ? env : env0) * R;
+    const TrailStore st = trail_store(p);
+    const long long gi = p.state_off + (owner ? env : env0);
     EnvState e = unpack_meta(make_uint2(0, 0));
     TrailCells g;
-    g.rec = rec; g.W = p.W; g.H = p.H; g.n[0] = g.n[1] = 0;
+    g.W = p.W; g.H = p.H; g.n[0] = g.n[1] = 0; g.cold = st.cold + gi * st.cw; g.dirty = 0; g.n_fresh = 0;
     if (owner) {
-        const uint4 hdr = *(const uint4*)rec;
+        const uint4 hdr = st.hot[gi];
         e = unpack_meta(make_uint2(hdr.x, hdr.y));
         g.n[0] = (int)(hdr.z & 0xFFFFu); g.n[1] = (int)(hdr.z >> 16);
+        if (MODE == MODE_STEP) g.load_hot(st, gi, kTrailHot);
+        if (MODE == MODE_OBSERVE) emit_extra(p, env);
     }
     __syncthreads();
     const int T = MODE == MODE_STEP ? p.T : 1;
     for (int t = 0; t < T; ++t) {
         if (MODE == MODE_STEP && owner) {
-            const uint4 a = *(const uint4*)(rec + 16), b = *(const uint4*)(rec + 32), c = *(const uint4*)(rec + 48);
-            g.hot[0] = a.x; g.hot[1] = a.y; g.hot[2] = a.z; g.hot[3] = a.w; g.hot[4] = b.x; g.hot[5] = b.y; g.hot[6] = b.z; g.hot[7] = b.w;
-            g.hot[8] = c.x; g.hot[9] = c.y; g.hot[10] = c.z; g.hot[11] = c.w;
-            g.n_fresh = 0;
             BoxRegs bx;
-            if (env_tick<MODE_STEP, false>(g, p, e, env, t, tid, bx)) { g.n[0] = g.n[1] = 0; }
-            else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) if (i < g.n_fresh) g.n[g.fresh_owner[i]] += 1;
-            }
+            if (env_tick<MODE_STEP, false>(g, p, e, env, t, tid, bx)) { g.n[0] = g.n[1] = 0; g.n_fresh = 0; }
+            else g.commit();
         }
         if (!(MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1)) continue;
+        if (MODE == MODE_STEP && owner) g.store_dirty(st, gi);  // the whole warp reads the lists back from memory below
         const size_t tick_off = (MODE == MODE_STEP && p.obs_every_tick) ? (size_t)t * (size_t)p.N * 2 * (size_t)P * (size_t)C * ES : 0;
         char* obase = (char*)p.obs + tick_off;
         __syncwarp();  // the entries appended in this tick (plain global stores of the owning lanes) are read by the whole warp below
@@ -214,10 +260,10 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
             }
             __syncwarp();
             // -- trail cells of both players (distinct cells), then the heads (P2 last, it wins a shared cell)
-            const uint32_t* words = (const uint32_t*)((const unsigned char*)p.grid + (size_t)senv * R + 16);
+            const long long si = p.state_off + senv;
             const int nmax = max(n1, n2);
             for (int k = lane; k < nmax; k += 32) {
-                const uint32_t v = __ldcg(words + k);  // L2 read: another lane of this warp may have appended the entry in this tick
+                const uint32_t v = __ldcg(st.word(si, k));  // L2 read: another lane of this warp may have appended the entry in this tick
 #pragma unroll
                 for (int pl2 = 0; pl2 < 2; ++pl2) {
                     if (k >= (pl2 ? n2 : n1)) continue;
@@ -241,14 +287,14 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
     }
     if (MODE == MODE_STEP && owner) {
         const uint2 m = pack_meta(e);
-        *(uint4*)rec = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
+        st.hot[gi] = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
     }
 }
 
 template <int OD, int LP, bool CP, int MODE>
 static int launch_trail_obs_one(StepParams p, cudaStream_t s) {
     // games per warp: aim at >= ~6 waves of CTAs (4 CTAs/SM resident), at most one game per lane
-    int gpw = p.N / (6 * 4 * 148 * 4);
+    int gpw = p.N / (6 * 4 * sm_count() * 4);
     gpw = gpw < 1 ? 1 : (gpw > 32 ? 32 : gpw);
     const int G = 4 * gpw;
     p.G = G;
@@ -288,14 +334,14 @@ int launch_step_trail(const StepParams& p, int mode, cudaStream_t s) {
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 
-// ---- export: render Tile.value grids / metadata from the records; import: rebuild the lists from grids ---------------
-__global__ void trail_export_kernel(const unsigned char* __restrict__ recs, int n, int W, int H, int8_t* tiles, int8_t* heads, uint8_t* alive,
-                                    uint8_t* done, uint8_t* winner, int32_t* ep_len) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= n) return;
-    const size_t R = trail_record_bytes(W, H);
-    const unsigned char* rec = recs + (size_t)env * R;
-    const uint4 hdr = *(const uint4*)rec;
+// ---- export: render Tile.value grids / metadata from the lists; import: rebuild the lists from grids ---------------
+__global__ void trail_export_kernel(const StepParams p, int8_t* tiles, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner, int32_t* ep_len) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.N) return;
+    const TrailStore st = trail_store(p);
+    const long long i = p.state_off + env;
+    const int W = p.W, H = p.H;
+    const uint4 hdr = st.hot[i];
     const EnvState e = unpack_meta(make_uint2(hdr.x, hdr.y));
     const int n1 = (int)(hdr.z & 0xFFFFu), n2 = (int)(hdr.z >> 16), Hc = H + 2, C = (W + 2) * (H + 2);
     if (tiles) {
@@ -304,15 +350,16 @@ __global__ void trail_export_kernel(const unsigned char* __restrict__ recs, int 
             const int r = c / Hc, q = c - r * Hc;
             t[c] = (r == 0 || r == W + 1 || q == 0 || q == H + 1) ? (int8_t)TRON_TILE_WALL : (int8_t)TRON_TILE_EMPTY;
         }
-        const unsigned short* ent = (const unsigned short*)(rec + 16);
-        for (int k = 0; k < max(n1, n2); ++k)
+        for (int k = 0; k < max(n1, n2); ++k) {
+            const uint32_t word = *st.word(i, k);
             for (int pl = 0; pl < 2; ++pl) {
                 if (k >= (pl ? n2 : n1)) continue;
-                const unsigned short v = ent[2 * k + pl];
+                const unsigned v = pl ? (word >> 16) : (word & 0xFFFFu);
                 const int r = v & 0x7F, c = v >> 8;
                 const bool slide = v & 0x80;
                 t[(r + 1) * Hc + c + 1] = (int8_t)(pl ? (slide ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY) : (slide ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY));
             }
+        }
         t[(e.r1 + 1) * Hc + e.c1 + 1] = TRON_TILE_P1_HEAD;
         t[(e.r2 + 1) * Hc + e.c2 + 1] = TRON_TILE_P2_HEAD;  // written second (reference game.py:205-214)
     }
@@ -322,43 +369,46 @@ __global__ void trail_export_kernel(const unsigned char* __restrict__ recs, int 
     if (winner) winner[env] = (e.flags >> TRON_FLAG_WINNER_SHIFT) & 3u;
     if (ep_len) ep_len[env] = e.k;
 }
-__global__ void trail_import_kernel(unsigned char* recs, int n, int W, int H, const int8_t* __restrict__ tiles, const int8_t* heads, const uint8_t* alive,
-                                    const uint8_t* done, const uint8_t* winner, const int32_t* ep_len) {
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= n) return;
-    const size_t R = trail_record_bytes(W, H);
-    unsigned char* rec = recs + (size_t)env * R;
-    uint4 hdr = *(const uint4*)rec;
+__global__ void trail_import_kernel(const StepParams p, const int8_t* __restrict__ tiles, const int8_t* heads, const uint8_t* alive, const uint8_t* done,
+                                    const uint8_t* winner, const int32_t* ep_len) {
+    const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.N) return;
+    const TrailStore st = trail_store(p);
+    const long long i = p.state_off + env;
+    const int W = p.W, H = p.H;
+    uint4 hdr = st.hot[i];
     if (tiles) {
         const int Hc = H + 2;
         const int8_t* t = tiles + (size_t)env * (W + 2) * (H + 2);
-        unsigned short* ent = (unsigned short*)(rec + 16);
         int n1 = 0, n2 = 0;
         for (int r = 0; r < W; ++r)
             for (int c = 0; c < H; ++c) {
                 const int v = t[(r + 1) * Hc + c + 1];
-                if (v == TRON_TILE_P1_BODY || v == TRON_TILE_P1_SLIDE) ent[2 * (n1++) + 0] = TrailCells::pack(r, c, v == TRON_TILE_P1_SLIDE);
-                else if (v == TRON_TILE_P2_BODY || v == TRON_TILE_P2_SLIDE) ent[2 * (n2++) + 1] = TrailCells::pack(r, c, v == TRON_TILE_P2_SLIDE);
+                if (v == TRON_TILE_P1_BODY || v == TRON_TILE_P1_SLIDE) ((unsigned short*)st.word(i, n1++))[0] = TrailCells::pack(r, c, v == TRON_TILE_P1_SLIDE);
+                else if (v == TRON_TILE_P2_BODY || v == TRON_TILE_P2_SLIDE) ((unsigned short*)st.word(i, n2++))[1] = TrailCells::pack(r, c, v == TRON_TILE_P2_SLIDE);
             }
         hdr.z = (uint32_t)n1 | ((uint32_t)n2 << 16);
     }
     uint32_t f = hdr.y & 0xFFu, k = hdr.y >> 16;
-    if (heads) hdr.x = ((const uint32_t*)heads)[env];
+    if (heads) {  // clamp to the representable range [-1, W] x [-1, H]
+        const int8_t* h = heads + 4 * env;
+        const int r1 = min(max((int)h[0], -1), W), c1 = min(max((int)h[1], -1), H), r2 = min(max((int)h[2], -1), W), c2 = min(max((int)h[3], -1), H);
+        hdr.x = (uint32_t)(uint8_t)r1 | ((uint32_t)(uint8_t)c1 << 8) | ((uint32_t)(uint8_t)r2 << 16) | ((uint32_t)(uint8_t)c2 << 24);
+    }
     if (alive) f = (f & ~3u) | (alive[2 * env] ? 1u : 0u) | (alive[2 * env + 1] ? 2u : 0u);
     if (done) f = (f & ~TRON_FLAG_DONE) | (done[env] ? TRON_FLAG_DONE : 0u);
     if (winner) f = (f & ~(3u << TRON_FLAG_WINNER_SHIFT)) | ((winner[env] & 3u) << TRON_FLAG_WINNER_SHIFT);
     if (ep_len) k = (uint32_t)ep_len[env] & 0xFFFFu;
     hdr.y = f | (k << 16);
-    *(uint4*)rec = hdr;
+    st.hot[i] = hdr;
 }
-int launch_trail_export(const void* recs, int n, int W, int H, int8_t* tiles, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner,
-                        int32_t* ep_len, cudaStream_t s) {
-    trail_export_kernel<<<(n + 127) / 128, 128, 0, s>>>((const unsigned char*)recs, n, W, H, tiles, heads, alive, done, winner, ep_len);
+int launch_trail_export(const StepParams& p, int8_t* tiles, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner, int32_t* ep_len, cudaStream_t s) {
+    trail_export_kernel<<<(p.N + 127) / 128, 128, 0, s>>>(p, tiles, heads, alive, done, winner, ep_len);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
-int launch_trail_import(void* recs, int n, int W, int H, const int8_t* tiles, const int8_t* heads, const uint8_t* alive, const uint8_t* done,
-                        const uint8_t* winner, const int32_t* ep_len, cudaStream_t s) {
-    trail_import_kernel<<<(n + 127) / 128, 128, 0, s>>>((unsigned char*)recs, n, W, H, tiles, heads, alive, done, winner, ep_len);
+int launch_trail_import(const StepParams& p, const int8_t* tiles, const int8_t* heads, const uint8_t* alive, const uint8_t* done, const uint8_t* winner,
+                        const int32_t* ep_len, cudaStream_t s) {
+    trail_import_kernel<<<(p.N + 127) / 128, 128, 0, s>>>(p, tiles, heads, alive, done, winner, ep_len);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 

@@ -34,8 +34,16 @@ struct StepParams {
     int N, W, H, Hc, C, G, layout;
     int T, obs_every_tick, auto_reset, slide_mode, action_dtype, spawn_mode;
     int P;  // planes written per player (lut planes + optional const plane)
+    int obs_es;  // bytes per observation element
     float r_base, r_tick, r_win, r_lose, r_draw, const_plane;
     PlaneTab tab[2][3];
+    void* obs_term;       // tron_step_args.obs_terminal: last frame of games that finished and were auto-reset in this call
+    float* extra;         // tron_step_args.extra [N,2,2] {degree, weight_p}
+    // dense (structure-of-arrays) state layouts (TRAIL hot arrays, BITS planes): the arrays hold state_N games and this launch's
+    // env 0 is entry state_off, so a chunked launch (host-buffer front end) addresses the same arrays as a whole-batch launch
+    long long state_off;
+    int state_N;
+    int variant;          // TRON_OPT_ENCODE_VARIANT
 };
 
 __device__ __forceinline__ int read_action(const void* actions, int dtype, size_t i) {
@@ -49,11 +57,13 @@ struct EnvState {
     int r1, c1, r2, c2;
     uint32_t flags;
     int k;  // ticks played in this episode
+    int tr1, tc1, tr2, tc2;  // heads of the game that just finished (valid when env_tick returned true in MODE_STEP)
 };
 __device__ __forceinline__ EnvState unpack_meta(uint2 m) {
     EnvState e;
     e.r1 = (int8_t)(m.x & 0xFF); e.c1 = (int8_t)((m.x >> 8) & 0xFF); e.r2 = (int8_t)((m.x >> 16) & 0xFF); e.c2 = (int8_t)(m.x >> 24);
     e.flags = m.y & 0xFFu; e.k = (int)(m.y >> 16);
+    e.tr1 = e.tc1 = e.tr2 = e.tc2 = 0;
     return e;
 }
 __device__ __forceinline__ uint2 pack_meta(const EnvState& e) {
@@ -87,8 +97,17 @@ __device__ __forceinline__ void box_set_spawn(BoxRegs& x, const EnvState& e) {
 struct ByteCells {  // int8 Tile.value grid, row-major (W+2) x (H+2), in shared memory or HBM
     int8_t* p;
     int Hc;
-    __device__ __forceinline__ int get(int r, int c) const { return p[(r + 1) * Hc + c + 1]; }
-    __device__ __forceinline__ void put(int r, int c, int tile) { p[(r + 1) * Hc + c + 1] = (int8_t)tile; }
+    int C;  // cells per game (range checks of the debug build)
+    __device__ __forceinline__ int get(int r, int c) const {
+        const int i = (r + 1) * Hc + c + 1;
+        if (!TRON_DCHECK(i >= 0 && i < C, DBG_CELL_INDEX)) return TRON_TILE_WALL;
+        return p[i];
+    }
+    __device__ __forceinline__ void put(int r, int c, int tile) {
+        const int i = (r + 1) * Hc + c + 1;
+        if (!TRON_DCHECK(i >= 0 && i < C, DBG_CELL_INDEX)) return;
+        p[i] = (int8_t)tile;
+    }
 };
 
 // ByteCells that also remembers what it wrote (at most two bodies, two slide tiles, two heads per tick), so that a kernel
@@ -96,12 +115,18 @@ struct ByteCells {  // int8 Tile.value grid, row-major (W+2) x (H+2), in shared 
 struct LoggedByteCells {
     int8_t* p;
     int Hc;
+    int C;
     int n;
     unsigned short idx[6];
     int8_t val[6];
-    __device__ __forceinline__ int get(int r, int c) const { return p[(r + 1) * Hc + c + 1]; }
+    __device__ __forceinline__ int get(int r, int c) const {
+        const int i = (r + 1) * Hc + c + 1;
+        if (!TRON_DCHECK(i >= 0 && i < C, DBG_CELL_INDEX)) return TRON_TILE_WALL;
+        return p[i];
+    }
     __device__ __forceinline__ void put(int r, int c, int tile) {
         const int i = (r + 1) * Hc + c + 1;
+        if (!TRON_DCHECK(i >= 0 && i < C, DBG_CELL_INDEX)) return;
         p[i] = (int8_t)tile;
 #pragma unroll
         for (int k = 0; k < 6; ++k)
@@ -112,9 +137,13 @@ struct LoggedByteCells {
 
 // One tick of the env whose cells start at `g`.  Updates `e` (fresh game state if it returns true = "rebuild this grid"),
 // writes reward/done/winner/ep_len for (tick t, env) and adds to the striped statistics.  TRACK maintains the dirty boxes.
+// pre_actions: the two actions already fetched (and range-folded by read_action) by a kernel that prefetches its inputs.
 template <int MODE, bool TRACK, class Cells>
-__device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState& e, long long env, int t, int tid, BoxRegs& bx) {
+__device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState& e, long long env, int t, int tid, BoxRegs& bx,
+                                         const int* pre_actions = nullptr) {
     bool do_reset = false;
+    (void)TRON_DCHECK(env >= 0 && env < p.N, DBG_ENV_OWNER);
+    (void)TRON_DCHECK(e.r1 >= -1 && e.r1 <= p.W && e.c1 >= -1 && e.c1 <= p.H && e.r2 >= -1 && e.r2 <= p.W && e.c2 >= -1 && e.c2 <= p.H, DBG_HEAD_RANGE);
     const unsigned long long genv = p.env_base + (unsigned long long)env;
     const unsigned long long ctr = p.counter + (p.counter_dev ? *p.counter_dev : 0ull) + (unsigned long long)t;
     const size_t tn = (size_t)t * (size_t)p.N + (size_t)env;
@@ -122,7 +151,9 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
         do_reset = p.env_mask ? p.env_mask[env] != 0 : true;
     } else {
         int a1, a2;
-        if (p.actions) {
+        if (pre_actions) {
+            a1 = pre_actions[0]; a2 = pre_actions[1];
+        } else if (p.actions) {
             a1 = read_action(p.actions, p.action_dtype, 2 * tn);
             a2 = read_action(p.actions, p.action_dtype, 2 * tn + 1);
         } else {
@@ -251,14 +282,34 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
             }
         }
     }
+    char4 tp_now = make_char4(0, 0, 0, 0);
+    bool tp_known = false;
     if (do_reset) {  // fresh game (reference game.py:70-91, util.py:70-78); the caller rebuilds the cells
         const char4 sp = p.spawn ? ((const char4*)p.spawn)[tn] : rng_spawn(p.seed, ctr, genv, p.W, p.H, p.spawn_mode);
+        e.tr1 = e.r1; e.tc1 = e.c1; e.tr2 = e.r2; e.tc2 = e.c2;
         e.r1 = sp.x; e.c1 = sp.y; e.r2 = sp.z; e.c2 = sp.w;
         e.flags = TRON_FLAG_ALIVE1 | TRON_FLAG_ALIVE2 | (TRACK ? (e.flags & TRON_FLAG_BOXES_VALID) : 0u);
         e.k = 0;
-        if (MODE == MODE_STEP && p.slide_mode == TRON_SLIDE_TEMPER && p.slide_params) ((char4*)p.slide_params)[env] = rng_temper(p.seed, ctr, genv);
+        // Game.__init__ draws weight x2 and degree for every fresh game (reference game.py:83,87), tron_reset included
+        if (p.slide_mode == TRON_SLIDE_TEMPER && p.slide_params) {
+            tp_now = rng_temper(p.seed, ctr, genv);
+            tp_known = true;
+            ((char4*)p.slide_params)[env] = tp_now;
+        }
+    }
+    if (p.extra && p.slide_params && (MODE != MODE_STEP || t == p.T - 1)) {  // [degree, weight_p] of the game the observation shows
+        if (!tp_known) tp_now = ((const char4*)p.slide_params)[env];
+        ((float4*)p.extra)[env] = make_float4((float)tp_now.x, (float)tp_now.y, (float)tp_now.x, (float)tp_now.z);
     }
     return do_reset;
+}
+
+// tron_observe: the side features of the current games (no tick runs in MODE_OBSERVE)
+__device__ __forceinline__ void emit_extra(const StepParams& p, long long env) {
+    if (p.extra && p.slide_params) {
+        const char4 tp = ((const char4*)p.slide_params)[env];
+        ((float4*)p.extra)[env] = make_float4((float)tp.x, (float)tp.y, (float)tp.x, (float)tp.z);
+    }
 }
 
 }  // namespace tron

@@ -53,6 +53,18 @@ class HistoryElement:
 _DELTA = ((-1, 0), (0, 1), (1, 0), (0, -1))
 
 
+def _takes_extra(act):
+    """does act(obs, extra) accept the side-feature argument?  (decided from the signature, never by catching TypeError)"""
+    import inspect
+    try:
+        params = list(inspect.signature(act).parameters.values())
+    except (TypeError, ValueError):
+        return True
+    if any(p.kind == p.VAR_POSITIONAL for p in params):
+        return True
+    return len([p for p in params if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]) >= 2
+
+
 class Game:
     def __init__(self, width, height, pps, mode=None, slide_pram=None):
         self.width = width
@@ -117,25 +129,30 @@ class Game:
     def degree_map(self):
         return np.full((_config.MAP_WIDTH + 2, _config.MAP_HEIGHT + 2), self.get_degree())
 
-    def _slide_tape(self, actions):
-        """Consume the global RNG exactly like game.py:163-178: one random.random() per player whose first move lands on a
-        free in-bounds cell (P2 sees P1's slide tile), P1 first.  Only the Bernoulli outcomes go to the GPU."""
-        codes = self.history[-1].map._codes.copy()
-        for i, pp in enumerate(self.pps):
-            codes[pp.position[0] + 1, pp.position[1] + 1] = 1 if i == 0 else 3
-        tape = [0, 0]
-        for i, pp in enumerate(self.pps):
-            r, c = pp.position[0] + _DELTA[actions[i]][0], pp.position[1] + _DELTA[actions[i]][1]
-            if 0 <= r < self.width and 0 <= c < self.height and codes[r + 1, c + 1] == 0:
-                rate = self.slide if self.mode == "ice" else self.get_rate(i)
-                if random.random() <= rate:
-                    tape[i] = 1
-                    codes[r + 1, c + 1] = 5 if i == 0 else 6
-        return np.array([tape], np.uint8)
+    def _slide_draw(self, codes, i, action):
+        """Consume the global RNG exactly like game.py:163-178 for player i: one random.random() iff its first move lands on a
+        free in-bounds cell of the scratch grid (P2 sees P1's slide tile).  Only the Bernoulli outcome goes to the GPU."""
+        pp = self.pps[i]
+        r, c = pp.position[0] + _DELTA[action][0], pp.position[1] + _DELTA[action][1]
+        if 0 <= r < self.width and 0 <= c < self.height and codes[r + 1, c + 1] == 0:
+            rate = self.slide if self.mode == "ice" else self.get_rate(i)
+            if random.random() <= rate:
+                codes[r + 1, c + 1] = 5 if i == 0 else 6
+                return 1
+        return 0
 
     # ------------------------------------------------------------------ ticks
     def next_frame(self, action_p1, action_p2, window=None):
         actions = [action_p1, action_p2]
+        sliding = self.mode in ("ice", "temper")
+        tape = [0, 0]
+        codes = None
+        if sliding and not self._finished:  # scratch grid of game.py:151-156: both old heads are bodies before anyone moves
+            codes = self.history[-1].map._codes.copy()
+            for i, pp in enumerate(self.pps):
+                codes[pp.position[0] + 1, pp.position[1] + 1] = 1 if i == 0 else 3
+        # the reference interleaves per player: move decision (a scripted player may draw from the global RNG), then that
+        # player's slide draw, P1 before P2 (game.py:158-198)
         for i, pp in enumerate(self.pps):
             if isinstance(pp.player, ACPlayer):
                 actions[i] = int(actions[i])
@@ -145,10 +162,11 @@ class Game:
                 actions[i] = pp.player.direction.value - 1
             else:
                 raise NotImplementedError("unsupported player type %r" % type(pp.player).__name__)
+            if codes is not None:
+                tape[i] = self._slide_draw(codes, i, actions[i])
         if self._finished:
             return True  # finished game: frozen (documented deviation)
-        tape = self._slide_tape(actions)[0] if self.mode in ("ice", "temper") else None
-        snap = self._env.step(actions, slide_tape=tape)
+        snap = self._env.step(actions, slide_tape=tape if sliding else None)
         self.history[-1].player_one_direction = self.pps[0].player.direction
         self.history[-1].player_two_direction = self.pps[1].player.direction
         self.history.append(HistoryElement(self._map_from_device(snap), None, None))
@@ -203,12 +221,9 @@ class Game:
                     if getattr(mdl, "wants_prob_map", False):  # MapNet-style input: extra constant plane (game.py:297)
                         x = torch.cat([x, torch.tensor(self.prob_map()).unsqueeze(0).float()], 0)
                         a = mdl.act(x.unsqueeze(0))
-                    else:
-                        extra = torch.tensor([self.get_multy(pid - 1)]).to(dev)
-                        try:
-                            a = mdl.act(x.unsqueeze(0), extra)
-                        except TypeError:
-                            a = mdl.act(x.unsqueeze(0))
+                    else:  # game.py:299,304: model gets [[degree, weight_p1]], model2 gets [[rate]]
+                        extra = torch.tensor([self.get_multy(0)] if pid == 1 else [[self.get_rate()]]).to(dev)
+                        a = mdl.act(x.unsqueeze(0), extra) if _takes_extra(mdl.act) else mdl.act(x.unsqueeze(0))
                     acts.append(int(a))
             if not self.next_frame(acts[0], acts[1], window):
                 break

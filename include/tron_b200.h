@@ -12,10 +12,13 @@
  *   tron/util.py:38-45     prob_map                 -> TRON_ENC_POPUP3_CONST (4th constant plane)
  *   tron/util.py:46-84     make_game (spawn rule)   -> tron_reset / auto-reset inside tron_step
  *   tron/util.py:87-94, DQN.py:224-241, DDQN.py:289-305   reward policies -> tron_reward_t
+ *   tron/game.py:137-139   Game.get_multy ([degree, weight]) -> tron_step_args.extra
  *   ACKTR.py:285-317       vector-env auto-reset contract -> tron_step(auto_reset=1)
  *   DDQN.py:90-110, DQN.py:63-64   epsilon-greedy   -> tron_select_actions
- *   DQN.py:81-132          ReplayMemory             -> replay_push / replay_gather / replay_sample_indices
- *   DDQN.py:167-203        ReplayBuffer             -> replay_push / replay_gather / replay_sample_indices
+ *   DQN.py:81-132          ReplayMemory             -> replay_push / replay_gather / replay_sample_indices / replay_sample_gather
+ *   DDQN.py:167-203        ReplayBuffer             -> replay_push / replay_gather / replay_sample_indices / replay_sample_gather
+ *   DDQN.py:264-308, DQN.py:198-252   per-transition replay fill of the training loops -> replay_frames (the tick kernel writes
+ *                          observations, rewards and done flags straight into the ring; replay_frames_sample_gather reads them back)
  *
  * Conventions
  *   - Every entry point is extern "C", returns 0 (TRON_OK) or a negative tron_status, never throws.
@@ -40,7 +43,7 @@
 extern "C" {
 #endif
 
-#define TRON_B200_ABI_VERSION 1
+#define TRON_B200_ABI_VERSION 2
 
 typedef void* tron_stream_t; /* cudaStream_t */
 
@@ -80,9 +83,14 @@ enum {
     TRON_LAYOUT_TILE8 = 0, /* int8 Tile.value per cell (any grid size, all modes) + 8-byte meta + 8-byte dirty boxes per env */
     TRON_LAYOUT_BITS10 = 1, /* 10x10 grids only, no slide modes: two 128-bit planes (trail occupancy, trail owner) over the
                               100 interior cells = 32 bytes per game; walls implicit, heads in the meta.  4.5x less state traffic. */
-    TRON_LAYOUT_TRAIL = 2  /* any grid, all modes: one record per game = 16-byte header + the list of trail cells both players
-                              left behind (capacity W*H each, 2 bytes per cell).  A game-tick touches the record's first 64
-                              bytes instead of a dense grid; observations are rendered in shared memory.  Made for large grids. */
+    TRON_LAYOUT_TRAIL = 2, /* any grid, all modes: per game a 16-byte header + the list of trail cells both players left behind
+                              (capacity W*H each, 2 bytes per cell).  The header and the first 12 list entries of every game (64
+                              bytes, "hot") are stored as four dense uint4 arrays [4][N] so that a tick streams them fully
+                              coalesced; the rest of each list lives in a per-game cold area touched only by long episodes.
+                              Observations are rendered without materialising a grid.  Made for large grids. */
+    TRON_LAYOUT_BITS = 3   /* grids with W*H <= 128, all modes (incl. ice/temper): three 128-bit planes over the interior cells
+                              (trail occupancy, trail owner, slide tile), stored as three dense uint4 arrays [3][N] = 48 bytes per
+                              game; walls implicit, heads in the meta.  The bit-plane path for config.py's GAME_MODE="temper". */
 };
 
 /* RNG spawn rules of make_game (tron/util.py:46-84) */
@@ -190,6 +198,15 @@ typedef struct tron_step_args {
     int32_t obs_every_tick; /* 1: obs is [T,N,2,P,W+2,H+2]; 0: obs (if any) holds the last tick only */
     /* with n_ticks>1: actions is [T,N,2] (or NULL -> RNG), spawn is [T,N,4] (or NULL -> RNG),
      * reward [T,N,2], done [T,N], winner [T,N], ep_len_out [T,N] (each may be NULL) */
+
+    /* ---- added in ABI version 2 ---- */
+    void* obs_terminal;   /* optional device buffer shaped and typed like `obs`: the rows of games that FINISHED in this call and were
+                             auto-reset receive the observation of the finished game's last frame -- what DDQN.py:270-308 stores as
+                             next_state of a terminal transition, while `obs` already shows the fresh game (ACKTR.py:309-310).  Rows
+                             of other games are left untouched.  TILE8 / BITS10 / BITS layouts, tron_step only.  NULL -> not written. */
+    float* extra;         /* optional device [N,2,2] f32: per player {degree, weight_p} of the game `obs` shows (Game.get_multy,
+                             tron/game.py:137-139) taken from slide_params; needs slide_params.  Written by tron_step,
+                             tron_step_many (last tick), tron_observe and tron_reset_ex. */
 } tron_step_args;
 
 /* ---- library ---- */
@@ -207,7 +224,8 @@ int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* gr
  * many cells run thread-per-game on HBM with dirty-box resets instead of staging whole grids (default 1024). */
 enum {
     TRON_OPT_SPARSE_MIN_CELLS = 1,
-    TRON_OPT_TILE_BYTES = 2 /* shared-memory budget of one tile of games in the generic-size fused kernel (default 18432) */
+    TRON_OPT_TILE_BYTES = 2, /* shared-memory budget of one tile of games in the generic-size fused kernel (default 18432) */
+    TRON_OPT_ENCODE_VARIANT = 3 /* tuning/experiments: observation store schedule of the bit-plane kernels (0 = default) */
 };
 int tron_set_option(int option, int64_t value);
 int tron_cells_per_env(int width, int height);
@@ -223,6 +241,10 @@ int tron_build_plane_tables(const int8_t lut6[6], int obs_enc, int8_t* tab /* [2
 int tron_reset(void* state, int n_envs, int width, int height, int layout, const int8_t* spawn, int spawn_mode,
                const uint8_t* env_mask, uint64_t seed, uint64_t counter, uint64_t env_id_base,
                tron_stream_t stream);
+/* tron_reset with the full argument block: additionally draws the per-game temper parameters (slide_mode TRON_SLIDE_TEMPER:
+ * slide_params[N,4] = {degree, weight1, weight2, 0}, Game.__init__ tron/game.py:83,87) for every env it resets and fills
+ * `extra`.  Uses state, geometry, layout, spawn, spawn_mode, seed, counter, env_id_base, slide_mode, slide_params, extra. */
+int tron_reset_ex(const tron_step_args* args, const uint8_t* env_mask, tron_stream_t stream);
 /* One tick of every env, fused with observation encoding, rewards, done/winner and auto-reset. */
 int tron_step(const tron_step_args* args, tron_stream_t stream);
 /* Observation of the current state only (no tick): uses state, obs, obs_dtype, obs_enc, lut, const_plane. */
@@ -291,10 +313,42 @@ int replay_push(const replay_ring* ring, uint64_t cursor, const void* state, con
 int replay_gather(const replay_ring* ring, const int64_t* idx, int64_t k, void* out_state,
                   void* out_next, int out_dtype, int64_t* out_action, float* out_reward,
                   float* out_done, tron_stream_t stream);
-/* k distinct slots uniform in [0,size) (random.sample without replacement), Floyd's algorithm on
- * Philox(seed; counter).  k <= 4096, k <= size. */
-int replay_sample_indices(int64_t size, int k, uint64_t seed, uint64_t counter, int64_t* idx,
+/* k distinct slots uniform in [0,size) (random.sample without replacement, DDQN.py:193, DQN.py:111-112): idx[i] = pi(i) where pi
+ * is a keyed pseudo-random PERMUTATION of [0,size) (6-round Feistel network on ceil(log2 size) bits, round keys from
+ * Philox(seed; counter), cycle-walking back into range).  Every index is computed independently, so any k <= size works and the
+ * same function runs inside replay_sample_gather / replay_frames_sample_gather without a separate launch. */
+int replay_sample_indices(int64_t size, int64_t k, uint64_t seed, uint64_t counter, int64_t* idx,
                           tron_stream_t stream);
+/* replay_sample_indices + replay_gather in ONE launch: row i of the outputs is transition pi(i) of the `size` valid ring slots
+ * [0,size).  out_idx: optional device [k] receiving the sampled slots. */
+int replay_sample_gather(const replay_ring* ring, int64_t size, int64_t k, uint64_t seed, uint64_t counter, void* out_state,
+                         void* out_next, int out_dtype, int64_t* out_action, float* out_reward, float* out_done,
+                         int64_t* out_idx, tron_stream_t stream);
+
+/* ---- frame-sharing replay ring (the batched training loops, DDQN.py:264-308 / DQN.py:198-252) ----
+ * A ring of S time slots; slot (t % S) holds, for all `rows` = 2N (env, player) pairs, the observation the policy saw at tick t,
+ * the action it took, the reward it got and the env's done flag.  next_state of transition (t, row) is the frame in slot
+ * (t+1) % S -- the same memory the next tick's state lives in -- unless the env finished at tick t: then it is the row of
+ * `terminal` the tick kernel filled through tron_step_args.obs_terminal.  The caller points tron_step's obs / reward / done /
+ * obs_terminal and tron_select_actions' output at the slot, so "push" moves no data at all. */
+typedef struct replay_frames {
+    uint32_t struct_size;
+    int32_t frame_elems; /* P*(W+2)*(H+2) */
+    int32_t frame_dtype; /* TRON_BF16 | TRON_F32 | TRON_I8 */
+    int32_t n_slots;     /* S >= 2 */
+    int64_t rows;        /* 2N: row = 2*env + player */
+    void* frames;        /* device [S, rows, frame_elems] */
+    void* terminal;      /* device [S, rows, frame_elems] or NULL (then next_state of a terminal transition is the reset frame) */
+    uint8_t* action;     /* device [S, rows] */
+    float* reward;       /* device [S, rows] */
+    uint8_t* done;       /* device [S, rows/2]: one flag per env */
+} replay_frames;
+/* Sample k distinct transitions uniformly among ticks [first_tick, first_tick + n_ticks) x rows (all of whose next frames must
+ * already be in the ring: n_ticks <= S-1) and gather them, one launch.  Outputs as replay_gather; out_idx (optional) receives
+ * tick * rows + row of each sample. */
+int replay_frames_sample_gather(const replay_frames* fr, int64_t first_tick, int64_t n_ticks, int64_t k, uint64_t seed,
+                                uint64_t counter, void* out_state, void* out_next, int out_dtype, int64_t* out_action,
+                                float* out_reward, float* out_done, int64_t* out_idx, tron_stream_t stream);
 
 /* ---- host-buffer front end (what a Game.step caller with numpy arrays binds to) ---- */
 typedef struct tron_host_env tron_host_env;
@@ -305,14 +359,30 @@ int tron_host_env_destroy(tron_host_env* env);
 /* spawn_host [N,4] or NULL (RNG); obs_host receives the initial observations (may be NULL). */
 int tron_host_env_reset(tron_host_env* env, const int8_t* spawn_host, void* obs_host);
 /* Host in: actions_host [N,2] u8, spawn_host [N,4] or NULL.  Host out (each may be NULL): obs, reward [N,2],
- * done [N], winner [N].  Copies are chunked and overlapped with the kernels; returns after all outputs landed. */
+ * done [N], winner [N].  One H2D copy of the inputs, the tick kernels chunk by chunk, the observation D2H copies chunk by chunk
+ * behind them on a dedicated copy stream and one D2H copy per scalar array; returns after all outputs landed. */
 int tron_host_env_step(tron_host_env* env, const uint8_t* actions_host, const int8_t* spawn_host,
                        void* obs_host, float* reward_host, uint8_t* done_host, uint8_t* winner_host);
+/* The same step split in two so that consecutive steps pipeline: _begin enqueues everything and returns at once (the
+ * host buffers belong to the library until the matching _wait); _wait blocks until the OLDEST outstanding step has landed.
+ * At most two steps may be outstanding (device observations are double-buffered: tick t+1 runs while tick t drains over PCIe). */
+int tron_host_env_step_begin(tron_host_env* env, const uint8_t* actions_host, const int8_t* spawn_host,
+                             void* obs_host, float* reward_host, uint8_t* done_host, uint8_t* winner_host);
+int tron_host_env_step_wait(tron_host_env* env);
 /* Device state pointer of a host env (for tron_export_grid). */
 void* tron_host_env_state(tron_host_env* env);
-/* Pinned host memory for the buffers above (plain malloc'd memory also works, slower). */
+/* Pinned host memory for the buffers above (plain malloc'd memory also works, slower).  Pages are placed on the NUMA node of
+ * the current CUDA device (the calling thread is moved onto the device's local CPUs while the pages are allocated). */
 int tron_host_alloc(void** ptr, size_t bytes);
 int tron_host_free(void* ptr);
+/* Measured PCIe ceiling of this process's device: `repeats` back-to-back cudaMemcpyAsync of `bytes` between tron_host_alloc
+ * memory and device memory (direction 0 = host->device, 1 = device->host), timed with CUDA events -> GB/s. */
+int tron_host_copy_bandwidth(size_t bytes, int direction, int repeats, double* gb_per_s);
+
+/* ---- debug build (libtron_b200_debug.so, -DTRON_DEBUG; tests only) ----
+ * Every computed cell index, trail-list position, ring slot and env ownership is range-checked on the device; a violation is
+ * counted (and the access skipped) instead of corrupting memory.  Release builds return TRON_ERR_UNSUPPORTED. */
+int tron_debug_violations(uint64_t* count, int32_t* first_code);
 
 #ifdef __cplusplus
 }

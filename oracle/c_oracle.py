@@ -100,9 +100,18 @@ class OracleEnv:
             self.counter += 1
         sp = None if spawn is None else np.ascontiguousarray(spawn, np.int8)
         mk = None if mask is None else np.ascontiguousarray(mask, np.uint8)
-        lib().oracle_reset(_p(self.state), self.N, self.W, self.H, _p(sp), self.spawn_mode, _p(mk), C.c_uint64(self.seed),
-                           C.c_uint64(counter), C.c_uint64(self.env_id_base))
+        a = self._args(spawn=_p(sp), counter=counter, obs_enc=abi.ENC_NONE)
+        rc = lib().oracle_reset_ex(C.byref(a), _p(mk))
+        assert rc == 0, rc
         return self.observe() if self.P else None
+
+    def extra(self):
+        """[N,2,2] f32 {degree, weight_p} of the current games (Game.get_multy)"""
+        x = np.zeros((self.N, 2, 2), np.float32)
+        x[:, 0, 0] = x[:, 1, 0] = self.slide_params[:, 0]
+        x[:, 0, 1] = self.slide_params[:, 1]
+        x[:, 1, 1] = self.slide_params[:, 2]
+        return x
 
     def observe(self):
         obs = self.new_obs()
@@ -111,8 +120,9 @@ class OracleEnv:
         assert rc == 0, rc
         return obs
 
-    def step(self, actions=None, spawn=None, slide_tape=None, counter=None):
-        """-> obs, reward[N,2], done[N], winner[N], ep_len[N]"""
+    def step(self, actions=None, spawn=None, slide_tape=None, counter=None, obs_terminal=None):
+        """-> obs, reward[N,2], done[N], winner[N], ep_len[N].  obs_terminal: array like obs; rows of games that finished
+        and were auto-reset receive the finished game's last frame."""
         if counter is None:
             counter = self.counter
             self.counter += 1
@@ -126,7 +136,7 @@ class OracleEnv:
         sl = None if slide_tape is None else np.ascontiguousarray(slide_tape, np.uint8)
         a = self._args(actions=_p(act), action_dtype=0 if act is None else dtype_code(act), obs=_p(obs),
                        reward=_p(reward), done=_p(done), winner=_p(winner), ep_len_out=_p(eplen), spawn=_p(sp),
-                       slide_tape=_p(sl), counter=counter)
+                       slide_tape=_p(sl), counter=counter, obs_terminal=_p(obs_terminal))
         rc = lib().oracle_step(C.byref(a))
         assert rc == 0, rc
         return obs, reward, done, winner, eplen
@@ -200,7 +210,7 @@ def select_actions(q, eps, seed, counter, base=0):
 
 def sample_indices(size, k, seed, counter):
     idx = np.zeros(k, np.int64)
-    rc = lib().oracle_replay_sample_indices(C.c_int64(size), k, C.c_uint64(seed), C.c_uint64(counter), _p(idx))
+    rc = lib().oracle_replay_sample_indices(C.c_int64(size), C.c_int64(k), C.c_uint64(seed), C.c_uint64(counter), _p(idx))
     assert rc == 0, rc
     return idx
 

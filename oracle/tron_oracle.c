@@ -119,6 +119,30 @@ int oracle_reset(void* state, int N, int W, int H, const int8_t* spawn, int spaw
     return 0;
 }
 
+/* [degree, weight_p] of the game an observation shows (Game.get_multy, game.py:137-139): extra[N][2][2] */
+static void write_extra(const tron_step_args* a, int e) {
+    if (!a->extra || !a->slide_params) return;
+    const int8_t* sp = a->slide_params + 4 * (size_t)e;
+    float* x = a->extra + 4 * (size_t)e;
+    x[0] = (float)sp[0]; x[1] = (float)sp[1]; x[2] = (float)sp[0]; x[3] = (float)sp[2];
+}
+/* tron_reset_ex: like oracle_reset, plus Game.__init__'s three draws (game.py:83,87) for every game that is reset */
+int oracle_reset_ex(const tron_step_args* a, const uint8_t* mask) {
+    const int N = a->n_envs, W = a->width, H = a->height, C = cells_of(W, H);
+    int8_t* grid = grid_of(a->state); tron_meta* meta = meta_of(a->state, N, W, H);
+    for (int e = 0; e < N; ++e) {
+        if (!mask || mask[e]) {
+            int8_t s[4];
+            const uint64_t env = a->env_id_base + (uint64_t)e;
+            if (a->spawn) memcpy(s, a->spawn + 4 * (size_t)e, 4); else rng_spawn(a->seed, a->counter, env, W, H, a->spawn_mode, s);
+            fresh_game(grid + (size_t)e * C, meta + e, W, H, s);
+            if (a->slide_mode == TRON_SLIDE_TEMPER && a->slide_params) rng_temper(a->seed, a->counter, env, a->slide_params + 4 * (size_t)e);
+        }
+        write_extra(a, e);
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------ observation encoding */
 /* Map.color (map.py:67-81) as a table over Tile.value+1; lut6 = {empty, wall, own body, enemy body, own head, enemy head} */
 static void color_table(const int8_t lut6[6], int player /*0|1*/, int8_t t[8]) {
@@ -174,7 +198,7 @@ int oracle_observe(const tron_step_args* a) {
     if (!P || !a->obs) return TRON_ERR_INVALID;
     int8_t tab[2 * 3 * 8]; const int LP = oracle_build_plane_tables(a->lut, a->obs_enc, tab);
     const int8_t* grid = grid_of(a->state);
-    for (int e = 0; e < N; ++e) encode_env(grid + (size_t)e * C, C, tab, LP, P, a->const_plane, a->obs, a->obs_dtype, (size_t)e);
+    for (int e = 0; e < N; ++e) { encode_env(grid + (size_t)e * C, C, tab, LP, P, a->const_plane, a->obs, a->obs_dtype, (size_t)e); write_extra(a, e); }
     return 0;
 }
 
@@ -191,7 +215,7 @@ typedef struct { uint64_t f[TRON_STATS_FIELDS]; } stat_acc;
 /* tick `t` of a (possibly multi-tick) call; per-tick arrays are offset by the caller */
 static void step_tick(const tron_step_args* a, uint64_t counter, const void* actions, const int8_t* spawn,
                       const uint8_t* slide_tape, void* obs, float* reward, uint8_t* done_out, uint8_t* winner_out,
-                      int32_t* eplen_out, stat_acc* st) {
+                      int32_t* eplen_out, stat_acc* st, int last_tick) {
     const int N = a->n_envs, W = a->width, H = a->height, C = cells_of(W, H), P = planes_of(a->obs_enc);
     int8_t* grid = grid_of(a->state); tron_meta* meta = meta_of(a->state, N, W, H);
     int8_t tab[2 * 3 * 8]; int LP = 0;
@@ -281,6 +305,8 @@ static void step_tick(const tron_step_args* a, uint64_t counter, const void* act
                 st->f[TRON_STAT_EPISODES]++; st->f[TRON_STAT_EP_TICKS] += (uint64_t)fin;
                 st->f[winner == 0 ? TRON_STAT_DRAWS : winner == 1 ? TRON_STAT_P1_WINS : TRON_STAT_P2_WINS]++;
                 if (a->auto_reset) { /* ACKTR.py:296-310: replaced by a fresh game; returned obs is the new game's */
+                    /* DDQN.py:270-308 stores the finished game's last frame as next_state of the terminal transition */
+                    if (P && a->obs_terminal) encode_env(g, C, tab, LP, P, a->const_plane, a->obs_terminal, a->obs_dtype, (size_t)e);
                     int8_t s[4];
                     if (spawn) memcpy(s, spawn + 4 * (size_t)e, 4); else rng_spawn(a->seed, counter, env, W, H, a->spawn_mode, s);
                     fresh_game(g, m, W, H, s);
@@ -293,6 +319,7 @@ static void step_tick(const tron_step_args* a, uint64_t counter, const void* act
         if (winner_out) winner_out[e] = winner;
         if (eplen_out) eplen_out[e] = fin;
         if (P && obs) encode_env(g, C, tab, LP, P, a->const_plane, obs, a->obs_dtype, (size_t)e);
+        if (last_tick) write_extra(a, e);
     }
 }
 
@@ -311,7 +338,7 @@ int oracle_step_many(const tron_step_args* a) {
         if (a->obs && P) obs = (a->obs_every_tick) ? (char*)a->obs + tt * N * 2 * P * C * dsize(a->obs_dtype) : (t == T - 1 ? a->obs : NULL);
         step_tick(a, a->counter + (a->counter_dev ? *a->counter_dev : 0) + (uint64_t)t, act, sp, sl, obs, a->reward ? a->reward + tt * N * 2 : NULL,
                   a->done ? a->done + tt * N : NULL, a->winner ? a->winner + tt * N : NULL,
-                  a->ep_len_out ? a->ep_len_out + tt * N : NULL, &st);
+                  a->ep_len_out ? a->ep_len_out + tt * N : NULL, &st, t == T - 1);
     }
     if (a->stats) for (int i = 0; i < TRON_STATS_FIELDS; ++i) a->stats[i] += st.f[i];
     return 0;
@@ -404,17 +431,61 @@ int oracle_replay_gather(const replay_ring* ring, const int64_t* idx, int64_t k,
     }
     return 0;
 }
-/* Floyd's sampling without replacement: for j = size-k .. size-1: t = U[0,j]; pick t unless already chosen, else j */
-int oracle_replay_sample_indices(int64_t size, int k, uint64_t seed, uint64_t counter, int64_t* idx) {
-    if (k > size || k > 4096) return TRON_ERR_INVALID;
-    for (int i = 0; i < k; ++i) {
-        const uint64_t j = (uint64_t)(size - k + i);
-        uint32_t r[4]; philox4x32_10(seed, counter, (uint64_t)i, TAG_SAMPLE, 0, r);
-        const uint64_t x = ((uint64_t)r[0] << 32) | r[1];
-        const uint64_t t = (uint64_t)(((unsigned __int128)x * (unsigned __int128)(j + 1)) >> 64);
-        int dup = 0;
-        for (int q = 0; q < i; ++q) dup |= (uint64_t)idx[q] == t;
-        idx[i] = (int64_t)(dup ? j : t);
+/* Uniform sampling WITHOUT replacement (random.sample, DDQN.py:193 / DQN.py:111-112) as a keyed pseudo-random permutation of
+ * [0,size): idx[i] = pi(i), pi = 6-round balanced Feistel network on 2*hb bits (2^(2hb) >= size) with round keys from
+ * Philox(seed; counter) and cycle-walking back into [0,size).  Same construction as the product's sampler (include/tron_b200.h). */
+typedef struct { uint32_t key[6]; uint32_t mask; int hb; uint64_t size; } feistel_perm;
+static feistel_perm feistel_make(uint64_t size, uint64_t seed, uint64_t counter) {
+    feistel_perm f; uint32_t a[4], b[4];
+    philox4x32_10(seed, counter, 0, TAG_SAMPLE, 0, a); philox4x32_10(seed, counter, 0, TAG_SAMPLE, 1, b);
+    f.key[0] = a[0]; f.key[1] = a[1]; f.key[2] = a[2]; f.key[3] = a[3]; f.key[4] = b[0]; f.key[5] = b[1];
+    int bits = 1;
+    while (bits < 62 && (1ull << bits) < size) ++bits;
+    f.hb = (bits + 1) >> 1;
+    f.mask = f.hb >= 32 ? 0xFFFFFFFFu : ((1u << f.hb) - 1u);
+    f.size = size;
+    return f;
+}
+static uint32_t feistel_mix(uint32_t v) { v *= 0x85EBCA6Bu; v ^= v >> 13; v *= 0xC2B2AE35u; v ^= v >> 16; return v; }
+static uint64_t feistel_apply(const feistel_perm* f, uint64_t i) {
+    uint64_t x = i;
+    do {
+        uint32_t L = (uint32_t)(x >> f->hb) & f->mask, R = (uint32_t)x & f->mask;
+        for (int r = 0; r < 6; ++r) { const uint32_t t = L ^ (feistel_mix(R ^ f->key[r]) & f->mask); L = R; R = t; }
+        x = ((uint64_t)L << f->hb) | R;
+    } while (x >= f->size);
+    return x;
+}
+int oracle_replay_sample_indices(int64_t size, int64_t k, uint64_t seed, uint64_t counter, int64_t* idx) {
+    if (k > size || k <= 0) return TRON_ERR_INVALID;
+    const feistel_perm f = feistel_make((uint64_t)size, seed, counter);
+    for (int64_t i = 0; i < k; ++i) idx[i] = (int64_t)feistel_apply(&f, (uint64_t)i);
+    return 0;
+}
+/* frame-sharing ring (include/tron_b200.h replay_frames): transition u = (tick, row); state = frames[tick % S][row], next_state =
+ * terminal[tick % S][row] if the env finished at that tick and terminal frames are kept, else frames[(tick+1) % S][row] */
+int oracle_replay_frames_sample_gather(const replay_frames* fr, int64_t first_tick, int64_t n_ticks, int64_t k, uint64_t seed,
+                                       uint64_t counter, void* out_s, void* out_s2, int out_dtype, int64_t* out_a, float* out_r,
+                                       float* out_d, int64_t* out_idx) {
+    const uint64_t total = (uint64_t)n_ticks * (uint64_t)fr->rows;
+    if (k <= 0 || (uint64_t)k > total || n_ticks > fr->n_slots - 1) return TRON_ERR_INVALID;
+    const feistel_perm f = feistel_make(total, seed, counter);
+    const size_t F = (size_t)fr->frame_elems;
+    for (int64_t i = 0; i < k; ++i) {
+        const uint64_t u = feistel_apply(&f, (uint64_t)i);
+        const int64_t tick = first_tick + (int64_t)(u / (uint64_t)fr->rows), r = (int64_t)(u % (uint64_t)fr->rows);
+        const size_t slot = (size_t)(tick % fr->n_slots), nslot = (size_t)((tick + 1) % fr->n_slots);
+        const uint8_t dn = fr->done[slot * (size_t)(fr->rows / 2) + (size_t)(r / 2)];
+        const size_t a0 = (slot * (size_t)fr->rows + (size_t)r) * F, b0 = (nslot * (size_t)fr->rows + (size_t)r) * F;
+        for (size_t j = 0; j < F; ++j) {
+            store_elem(out_s, out_dtype, (size_t)i * F + j, load_as_f32(fr->frames, fr->frame_dtype, a0 + j));
+            store_elem(out_s2, out_dtype, (size_t)i * F + j,
+                       (dn && fr->terminal) ? load_as_f32(fr->terminal, fr->frame_dtype, a0 + j) : load_as_f32(fr->frames, fr->frame_dtype, b0 + j));
+        }
+        out_a[i] = fr->action[slot * (size_t)fr->rows + (size_t)r];
+        out_r[i] = fr->reward[slot * (size_t)fr->rows + (size_t)r];
+        out_d[i] = (float)dn;
+        if (out_idx) out_idx[i] = tick * fr->rows + r;
     }
     return 0;
 }

@@ -8,7 +8,9 @@ import os
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtron_b200.so")
+# TRON_B200_DEBUG=1 selects the range-checked build (libtron_b200_debug.so, tests only)
+DEBUG = os.environ.get("TRON_B200_DEBUG", "0") == "1"
+LIB_PATH = os.path.join(_HERE, "libtron_b200_debug.so" if DEBUG else "libtron_b200.so")
 
 
 class TronError(RuntimeError):
@@ -65,8 +67,8 @@ def load():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise TronError("libtron_b200.so is not built (%s); run `python __graft_entry__.py build` -- "
-                            "there is no CPU fallback" % LIB_PATH)
+            raise TronError("%s is not built (%s); run `python __graft_entry__.py build` -- "
+                            "there is no CPU fallback" % (os.path.basename(LIB_PATH), LIB_PATH))
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)

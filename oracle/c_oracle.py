@@ -269,3 +269,21 @@ def minimax_actions(env, player, tie_mode=0, counter=0, want_values=False):
                                       C.c_uint64(env.env_id_base), _p(act), _p(vals))
     assert rc == 0, rc
     return (act, vals) if want_values else act
+
+
+def frames_sample_gather(frames, terminal, action, reward, done, frame_dtype, first_tick, n_ticks, k, seed, counter, out_dtype=abi.F32):
+    """oracle of replay_frames_sample_gather: frames/terminal [S, rows, F] (terminal may be None), action u8 [S, rows],
+    reward f32 [S, rows], done u8 [S, rows/2] -> (s, a, r, s2, d, idx)"""
+    S, rows, F = frames.shape
+    frames = np.ascontiguousarray(frames); action = np.ascontiguousarray(action, np.uint8)
+    reward = np.ascontiguousarray(reward, np.float32); done = np.ascontiguousarray(done, np.uint8)
+    terminal = None if terminal is None else np.ascontiguousarray(terminal)
+    fr = abi.ReplayFrames(struct_size=C.sizeof(abi.ReplayFrames), frame_elems=F, frame_dtype=frame_dtype, n_slots=S, rows=rows,
+                          frames=_p(frames).value, terminal=None if terminal is None else _p(terminal).value,
+                          action=_p(action).value, reward=_p(reward).value, done=_p(done).value)
+    s = np.zeros((k, F), NP_OF[out_dtype]); s2 = np.zeros_like(s)
+    a = np.zeros(k, np.int64); r = np.zeros(k, np.float32); d = np.zeros(k, np.float32); idx = np.zeros(k, np.int64)
+    rc = lib().oracle_replay_frames_sample_gather(C.byref(fr), C.c_int64(first_tick), C.c_int64(n_ticks), C.c_int64(k), C.c_uint64(seed),
+                                                  C.c_uint64(counter), _p(s), _p(s2), out_dtype, _p(a), _p(r), _p(d), _p(idx))
+    assert rc == 0, rc
+    return s, a, r, s2, d, idx

@@ -1,5 +1,6 @@
-"""TRON_LAYOUT_BITS10 (two 128-bit planes per 10x10 game) must be indistinguishable from the int8 layout through the
-API: the same golden fixtures and oracle comparisons as tests/test_gpu_parity.py, bit for bit, including exported grids."""
+"""The bit-plane layouts -- TRON_LAYOUT_BITS10 (two 128-bit planes per 10x10 game, game-major) and TRON_LAYOUT_BITS (three dense
+plane arrays, any W*H <= 128, slide modes included) -- must be indistinguishable from the int8 layout through the API: the same
+golden fixtures and oracle comparisons as tests/test_gpu_parity.py, bit for bit, including exported grids."""
 import numpy as np
 import pytest
 
@@ -12,17 +13,21 @@ from tron_b200 import abi  # noqa: E402
 from _golden import digest_with, load_json, load_npz, ragged_to_tapes  # noqa: E402
 from _gpu import GpuEnvNumpy, assert_same_state, assert_same_step, make_pair  # noqa: E402
 
-L = "bits10"
+@pytest.fixture(params=["bits10", "bits"])
+def L(request):
+    return request.param
 
 
-def one_env(W, **kw):
-    kw.setdefault("obs_dtype", abi.I8); kw.setdefault("auto_reset", False)
-    return GpuEnvNumpy(1, W, W, layout=L, **kw)
+def one_env_of(L):
+    def one_env(W, **kw):
+        kw.setdefault("obs_dtype", abi.I8); kw.setdefault("auto_reset", False)
+        return GpuEnvNumpy(1, W, W, layout=L, **kw)
+    return one_env
 
 
-def test_kat_table_bits10():
+def test_kat_table_bits10(L):
     for name, case in load_json("kat.json").items():
-        env = one_env(10)
+        env = one_env_of(L)(10)
         obs = env.reset(spawn=np.array([case["spawn"]], np.int8))
         for t, snap in enumerate(case["ticks"]):
             if t > 0:
@@ -35,13 +40,13 @@ def test_kat_table_bits10():
 
 
 @pytest.mark.parametrize("seed", [0, 1])
-def test_digest_bits10(seed):
+def test_digest_bits10(L, seed):
     want = load_json("digests.json")[str(seed)]
-    got = digest_with(one_env, seed, 1000)
+    got = digest_with(one_env_of(L), seed, 1000)
     assert got[0] == want["sha256"] and got[1] == want["steps"] and got[2] == want["wins"]
 
 
-def test_full_trajectories_bits10():
+def test_full_trajectories_bits10(L):
     tr = load_npz("traj.npz")
     length = tr["length"]; G = len(length)
     tape, _, row = ragged_to_tapes(length, tr["actions"])
@@ -61,7 +66,7 @@ def test_full_trajectories_bits10():
 
 @pytest.mark.parametrize("dt,enc,ticks", [(abi.BF16, abi.ENC_LUT1, 256), (abi.F32, abi.ENC_LUT1, 48), (abi.I8, abi.ENC_LUT1, 48),
                                           (abi.BF16, abi.ENC_POPUP3, 48), (abi.F32, abi.ENC_POPUP3_CONST, 32), (abi.BF16, abi.ENC_NONE, 64)])
-def test_config2_4096_envs_tapes_bits10(dt, enc, ticks):
+def test_config2_4096_envs_tapes_bits10(L, dt, enc, ticks):
     N = 4096
     rng = np.random.default_rng(0)
     g, o = make_pair(N, 10, 10, layout=L, obs_dtype=dt, obs_enc=enc, const_plane=5.0, reward="ddqn")
@@ -88,7 +93,7 @@ def test_config2_4096_envs_tapes_bits10(dt, enc, ticks):
 
 
 @pytest.mark.parametrize("N", [1, 127, 129, 5000])
-def test_rng_mode_long_episodes_and_tails_bits10(N):
+def test_rng_mode_long_episodes_and_tails_bits10(L, N):
     g, o = make_pair(N, 10, 10, layout=L, obs_dtype=abi.BF16, seed=77, env_id_base=11, auto_reset=True)
     assert np.array_equal(g.reset(), o.reset())
     for t in range(40):
@@ -96,7 +101,7 @@ def test_rng_mode_long_episodes_and_tails_bits10(N):
     assert_same_state(g, o)
 
 
-def test_long_games_fill_the_board_bits10():
+def test_long_games_fill_the_board_bits10(L):
     """wall-avoiding tape from the reference fixtures -> long trails crossing the 64-bit word boundary"""
     tr = load_npz("traj.npz")
     length = tr["length"]
@@ -114,7 +119,7 @@ def test_long_games_fill_the_board_bits10():
         assert_same_state(g, o, "tick %d" % t)
 
 
-def test_step_many_frozen_bad_actions_masked_reset_bits10():
+def test_step_many_frozen_bad_actions_masked_reset_bits10(L):
     N, T = 3000, 24
     rng = np.random.default_rng(3)
     g, o = make_pair(N, 10, 10, layout=L, obs_dtype=abi.BF16, seed=11)
@@ -136,7 +141,7 @@ def test_step_many_frozen_bad_actions_masked_reset_bits10():
     assert_same_state(g, o)
 
 
-def test_export_import_round_trip_and_cross_layout():
+def test_export_import_round_trip_and_cross_layout(L):
     N = 2000
     a = GpuEnvNumpy(N, 10, 10, obs_dtype=abi.I8, seed=5, layout=L)
     b = GpuEnvNumpy(N, 10, 10, obs_dtype=abi.I8, seed=5, layout="tile8")
@@ -156,7 +161,7 @@ def test_export_import_round_trip_and_cross_layout():
             assert np.array_equal(x, y)
 
 
-def test_sharding_and_host_env_bits10():
+def test_sharding_and_host_env_bits10(L):
     from tron_b200.batch_env import HostTron
     N = 2048
     full = GpuEnvNumpy(N, 10, 10, obs_dtype=abi.I8, seed=21, layout=L)
@@ -180,12 +185,61 @@ def test_sharding_and_host_env_bits10():
     h.close()
 
 
-def test_bits10_refuses_what_it_cannot_represent():
+def test_bit_layouts_refuse_what_they_cannot_represent():
     from tron_b200 import _lib
     from tron_b200.batch_env import BatchedTron
     with pytest.raises(_lib.TronError):
-        BatchedTron(16, 12, 12, layout=L)
-    env = BatchedTron(16, 10, 10, layout=L, slide_mode="ice")
+        BatchedTron(16, 12, 12, layout="bits10")
+    with pytest.raises(_lib.TronError):
+        BatchedTron(16, 12, 11, layout="bits")  # 132 cells > 128 bits
+    env = BatchedTron(16, 10, 10, layout="bits10", slide_mode="ice")
     env.reset()
     with pytest.raises(_lib.TronError):
         env.step()
+
+
+# ------------------------------------------------------------------ TRON_LAYOUT_BITS only: slide modes and other boards
+def test_slide_tape_fixture_bits():
+    """reference-generated ice-mode trajectories (explicit Bernoulli tape) on the three-plane layout"""
+    sl = load_npz("slide.npz")
+    W = int(sl["W"]); length = sl["length"]; G = len(length)
+    tape, stape, row = ragged_to_tapes(length, sl["actions"], sl["slide"])
+    env = GpuEnvNumpy(G, W, W, obs_dtype=abi.I8, auto_reset=False, slide_mode=abi.SLIDE_TAPE, layout="bits")
+    env.reset(spawn=sl["spawn"])
+    for t in range(tape.shape[0]):
+        obs, rew, done, winner, _ = env.step(tape[t], slide_tape=stape[t])
+        live = row[t + 1] >= 0
+        r = row[t + 1][live]
+        assert (env.export()["tiles"][live] == sl["tiles"][r]).all()
+        assert (obs[live, 0, 0] == sl["obs1"][r]).all() and (obs[live, 1, 0] == sl["obs2"][r]).all()
+        assert (done[live] == sl["done"][r]).all() and (winner[live] == sl["winner"][r]).all()
+
+
+@pytest.mark.parametrize("mode,rate", [(abi.SLIDE_ICE, 0.15), (abi.SLIDE_ICE, 0.6), (abi.SLIDE_TEMPER, 0.0)])
+@pytest.mark.parametrize("dt,enc", [(abi.I8, abi.ENC_LUT1), (abi.BF16, abi.ENC_POPUP3), (abi.F32, abi.ENC_POPUP3_CONST), (abi.BF16, abi.ENC_NONE)])
+def test_slide_rng_modes_bits(mode, rate, dt, enc):
+    N = 3000
+    g, o = make_pair(N, 10, 10, layout="bits", obs_dtype=dt, obs_enc=enc, seed=99, slide_mode=mode, slide_rate=rate, const_plane=5.0)
+    a, b = g.reset(), o.reset()
+    if enc != abi.ENC_NONE:
+        assert np.array_equal(a, b)
+    slid = False
+    for t in range(40):
+        assert_same_step(g.step(), o.step(), "tick %d" % t)
+        slid |= bool((o.export()["tiles"] >= 5).any())
+    assert slid
+    assert_same_state(g, o)
+    if mode == abi.SLIDE_TEMPER:
+        assert np.array_equal(g.env.slide_params.cpu().numpy(), o.slide_params)
+
+
+@pytest.mark.parametrize("W,H,N", [(3, 3, 1000), (5, 5, 777), (7, 7, 4096), (11, 11, 130), (6, 11, 500), (8, 16, 2049), (2, 64, 300), (16, 8, 129)])
+@pytest.mark.parametrize("dt", [abi.BF16, abi.F32, abi.I8])
+def test_other_boards_bits(W, H, N, dt):
+    g, o = make_pair(N, W, H, layout="bits", obs_dtype=dt, seed=W * 100 + H, slide_mode=abi.SLIDE_ICE, slide_rate=0.3)
+    assert np.array_equal(g.reset(), o.reset())
+    for t in range(24):
+        assert_same_step(g.step(), o.step(), "tick %d" % t)
+    assert_same_step(g.step_many(6), o.step_many(6))
+    assert_same_state(g, o)
+    assert np.array_equal(g.stats, o.stats)

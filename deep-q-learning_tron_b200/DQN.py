@@ -79,48 +79,96 @@ class ReplayMemory(object):
         return 0 if self._ring is None else len(self._ring)
 
 
-def train(model=None, n_envs=4096, iterations=100, learn_steps_per_iter=1, device="cuda", seed=0, log=None):
-    """Batched restatement of DQN.train (DQN.py:135-309): self-play with the survivor reward (step index / 100 / -25 / 0),
-    1-plane observations, one smooth-L1 learn step per cycle on a uniform sample, target r or r + gamma * max Q(s')."""
+def learn_step(model, optimizer, batch):
+    """One DQN learn step as in the reference's train() (DQN.py:263-292): predicted Q of the taken action, target r for a terminal
+    transition else r + gamma * max_a Q(s', a) (same net, detached), smooth-L1 loss, one optimizer step.
+    batch = (old_state [k,...], action i64 [k,1], reward f32 [k,1], new_state, terminal f32 [k,1]).  -> detached loss"""
     import torch.nn.functional as F
+    s, a, r, s2, d = batch
+    pred = model(s).gather(1, a).sum(dim=1)
+    nxt = model(s2)
+    target = (r.squeeze(1) + (1 - d.squeeze(1)) * model.gamma * nxt.max(1)[0]).detach()
+    loss = F.smooth_l1_loss(pred, target)
+    model.zero_grad()
+    loss.backward()
+    optimizer.step()
+    return loss.detach()
+
+
+def train(model=None, n_envs=4096, iterations=100, learn_steps_per_iter=1, device="cuda", seed=0, log=None, layout="auto", replay="frames",
+          save_every=0, save_dir="save", on_cycle=None, timings=None):
+    """Batched restatement of DQN.train (DQN.py:135-309): self-play with the survivor reward (step index / 100 / -25 / 0),
+    1-plane observations, one smooth-L1 learn step per cycle on a uniform sample, target r or r + gamma * max Q(s').
+
+    replay="frames": the tick kernel fills a frame-sharing ring (no push); "ring": explicit transitions through replay_push.
+    save_every: write the reference's checkpoint (save/DQN.bak, DQN.py:295) every that many cycles.
+    on_cycle(cycle, stats): the numbers the reference logs per cycle (DQN.py:296-306): loss, p1 win rate, mean duration.
+    timings: optional dict receiving device times in ms summed over all ticks (q_forward, env_replay, learn)."""
+    import os
     from Net.DQNNet import Net
+    from tron_b200.replay import FrameRing
     model = model or Net(in_planes=1, batch_size=BATCH_SIZE, gamma=GAMMA).to(device)
     opt = torch.optim.Adam(model.parameters())
-    env = tron_b200.BatchedTron(n_envs, 10, 10, device=device, obs_dtype=torch.float32, obs_enc="lut1", reward="survivor", seed=seed)
-    mem = ReplayMemory(max(MEM_CAPACITY, 2 * n_envs * GAME_CYCLE), device=device)
-    obs = env.reset()
+    env = tron_b200.BatchedTron(n_envs, 10, 10, device=device, obs_dtype=torch.float32, obs_enc="lut1", reward="survivor", seed=seed, layout=layout)
+    rows = 2 * n_envs
+    frames = mem = None
+    if replay == "frames":  # at least the reference's capacity (DQN.py:32) and one cycle of ticks
+        frames = FrameRing(env, max(GAME_CYCLE + 1, min(64, -(-MEM_CAPACITY // rows) + 1)), keep_terminal=True, seed=seed)
+        obs = frames.begin()
+    else:
+        mem = ReplayMemory(max(MEM_CAPACITY, rows * GAME_CYCLE), device=device)
+        obs = env.reset()
     epsilon = float(EPSILON_START)
     losses = []
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    t_fwd = t_env = 0.0
+    events, learn_events = [], []
+    last_stats = env.stats_dict()
     for it in range(iterations):
         for _ in range(GAME_CYCLE):
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
             with torch.no_grad():
-                q = model(obs.view(2 * n_envs, 1, 12, 12))
+                q = model(obs.view(rows, 1, 12, 12))
             ev[1].record()
-            act = env.select_actions(q, epsilon, counter=env.counter)
-            res = env.step(act)
-            mem.push_batch(obs.view(2 * n_envs, 1, 12, 12), act.view(-1), res.obs.view(2 * n_envs, 1, 12, 12), res.reward.view(-1), res.done, done_stride=2)
-            obs = res.obs
+            if frames is not None:
+                env.select_actions(q, epsilon, counter=env.counter, out=frames.actions_slot().view(-1))
+                obs = frames.step().obs
+            else:
+                act = env.select_actions(q, epsilon, counter=env.counter)
+                term = obs.clone()
+                res = env.step(act, obs_terminal=term)
+                nxt = torch.where(res.done.view(-1, 1, 1, 1, 1).bool(), term, res.obs)  # a finished game's new_state is its last frame (DQN.py:205-252)
+                mem.push_batch(obs.view(rows, 1, 12, 12), act.view(-1), nxt.view(rows, 1, 12, 12), res.reward.view(-1), res.done, done_stride=2)
+                obs = res.obs
             ev[2].record()
-            if log:
-                torch.cuda.synchronize()
-                t_fwd += ev[0].elapsed_time(ev[1]); t_env += ev[1].elapsed_time(ev[2])
+            events.append(ev)
             if epsilon * DECAY_RATE > ESPILON_END:
                 epsilon *= DECAY_RATE
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for _ in range(learn_steps_per_iter):
-            s, a, r, s2, d = mem.sample_batch(min(len(mem), model.batch_size))
-            pred = model(s).gather(1, a).squeeze(1)
-            with torch.no_grad():
-                target = r.squeeze(1) + (1 - d.squeeze(1)) * model.gamma * model(s2).max(1)[0]
-            loss = F.smooth_l1_loss(pred, target)
-            model.zero_grad()
-            loss.backward()
-            opt.step()
-            losses.append(float(loss.detach()))
-        if log:
+            have = len(frames) if frames is not None else len(mem)
+            k = min(have, model.batch_size)
+            batch = frames.sample(k) if frames is not None else mem.sample_batch(k)
+            losses.append(learn_step(model, opt, batch))
+        e1.record()
+        learn_events.append((e0, e1))
+        if save_every and (it + 1) % save_every == 0:
+            os.makedirs(save_dir, exist_ok=True)
+            torch.save(model.state_dict(), os.path.join(save_dir, "DQN.bak"))
+        if on_cycle is not None or log:
             st = env.stats_dict()
-            st.update(q_forward_ms_per_tick=t_fwd / ((it + 1) * GAME_CYCLE), env_replay_ms_per_tick=t_env / ((it + 1) * GAME_CYCLE))
-            log(it, losses[-1], st)
+            d = {k: st[k] - last_stats[k] for k in st}
+            last_stats = st
+            info = dict(loss=float(losses[-1]), p1_winrate=d["p1_wins"] / max(1, d["episodes"]), duration=d["ep_ticks"] / max(1, d["episodes"]),
+                        episodes=d["episodes"], p1_wins=d["p1_wins"], p2_wins=d["p2_wins"], draws=d["draws"], epsilon=epsilon)
+            if on_cycle is not None:
+                on_cycle(it + 1, info)
+            if log:
+                log(it, info["loss"], st)
+    torch.cuda.synchronize()
+    losses = [float(l) for l in losses]
+    if timings is not None:
+        timings.update(ticks=len(events), q_forward_ms=sum(e[0].elapsed_time(e[1]) for e in events),
+                       env_replay_ms=sum(e[1].elapsed_time(e[2]) for e in events), learn_ms=sum(a.elapsed_time(b) for a, b in learn_events),
+                       learn_steps=len(losses), replay=replay, layout=env.layout)
     return model, losses

@@ -54,14 +54,16 @@ class BatchedTron:
     reward: name in abi.REWARD_POLICIES or a 5-tuple (step_base, step_per_tick, win, lose, draw).
     layout: "tile8" (int8 grid, default), "bits10" (32-byte bit planes, 10x10 without slide modes), "bits" (48-byte bit planes, any
     board with W*H <= 128, every mode), "trail" (trail lists, made for pure ticks on large grids) or "auto" (the fastest one that fits).
-    With slide_mode="temper" the per-game [degree, weight] side features (Game.get_multy, tron/game.py:137-139) of the games the
-    latest observation shows are kept in `self.extra` ([N,2,2] f32: per player {degree, weight_p}).
+    game_params: keep the per-game parameters Game.__init__ draws for every game (weight x2, degree; tron/game.py:83,87) in
+    `self.slide_params` ([N,4] int8 {degree, weight1, weight2, 0}) and the [degree, weight] side features of the games the latest
+    observation shows (Game.get_multy, tron/game.py:137-139) in `self.extra` ([N,2,2] f32: per player {degree, weight_p}).
+    Default: only with slide_mode="temper" (which needs them for the slip rate).
     """
 
     def __init__(self, n_envs, width=10, height=10, device="cuda", obs_dtype=torch.bfloat16, obs_enc="lut1", lut=None,
                  const_plane=0.0, reward="ddqn", auto_reset=True, seed=0, env_id_base=0, slide_mode=None,
                  slide_rate=0.15, collect_stats=True, layout="tile8", spawn_mode="uniform",
-                 policy="uniform", policy_epsilon=0.0):
+                 policy="uniform", policy_epsilon=0.0, game_params=None):
         _lib.require_cuda()
         self.lib = _lib.load()
         if layout == "auto":
@@ -94,8 +96,11 @@ class BatchedTron:
         with torch.cuda.device(self.device):
             self.state = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
             self.stats = torch.zeros(abi.STATS_SLOTS * abi.STATS_FIELDS, dtype=torch.int64, device=self.device) if collect_stats else None
-            self.slide_params = (torch.zeros((self.N, 4), dtype=torch.int8, device=self.device)
-                                 if self.slide_mode == abi.SLIDE_TEMPER else None)
+            if game_params is None:
+                game_params = self.slide_mode == abi.SLIDE_TEMPER
+            if self.slide_mode == abi.SLIDE_TEMPER and not game_params:
+                raise ValueError("slide_mode='temper' needs game_params")
+            self.slide_params = torch.zeros((self.N, 4), dtype=torch.int8, device=self.device) if game_params else None
             self.extra = torch.zeros((self.N, 2, 2), dtype=torch.float32, device=self.device) if self.slide_params is not None else None
 
     # ------------------------------------------------------------------ buffers

@@ -290,8 +290,8 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
         e.r1 = sp.x; e.c1 = sp.y; e.r2 = sp.z; e.c2 = sp.w;
         e.flags = TRON_FLAG_ALIVE1 | TRON_FLAG_ALIVE2 | (TRACK ? (e.flags & TRON_FLAG_BOXES_VALID) : 0u);
         e.k = 0;
-        // Game.__init__ draws weight x2 and degree for every fresh game (reference game.py:83,87), tron_reset included
-        if (p.slide_mode == TRON_SLIDE_TEMPER && p.slide_params) {
+        // Game.__init__ draws weight x2 and degree for every fresh game whatever the mode (reference game.py:83,87), tron_reset included
+        if (p.slide_params) {
             tp_now = rng_temper(p.seed, ctr, genv);
             tp_known = true;
             ((char4*)p.slide_params)[env] = tp_now;

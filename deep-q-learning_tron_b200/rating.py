@@ -6,32 +6,46 @@ import torch
 from .batch_env import BatchedTron
 
 
+def _takes_extra(fn):
+    """does fn(obs, extra) accept the side-feature argument?  Decided from the signature, never by catching TypeError."""
+    import inspect
+    try:
+        params = list(inspect.signature(fn).parameters.values())
+    except (TypeError, ValueError):
+        return False
+    if any(p.kind == p.VAR_POSITIONAL for p in params):
+        return True
+    return len([p for p in params if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)]) >= 2
+
+
 @torch.no_grad()
 def play_matches(model1, model2=None, n_games=10000, width=10, height=10, gamemode=None, slide=0.15, obs_enc="popup3",
-                 obs_dtype=torch.float32, device="cuda", seed=0, max_ticks=None, spawn_mode="fair"):
+                 obs_dtype=torch.float32, device="cuda", seed=0, max_ticks=None, spawn_mode="fair", layout="auto"):
     """Play n_games games of model1 (player 1) against model2 (player 2, default: model1).
 
-    A model is anything with `.act(obs[n, P, W+2, H+2]) -> n actions` (like the reference's nets), a callable doing the same, or
-    the string "minimax" for the batched scripted opponent (ACKTR.py:409-421 rates the agent against it).
+    A model is anything with `.act(obs[n, P, W+2, H+2][, extra]) -> n actions` (like the reference's nets), a callable doing the
+    same, or the string "minimax" for the batched scripted opponent (ACKTR.py:409-421 rates the agent against it).  Like
+    Game.main_loop (tron/game.py:296-304), model1 receives extra = [[degree, weight_1]] per game ([n,2] f32, Game.get_multy(0)) and
+    model2 receives extra = [[rate]] ([n,1] f32, Game.get_rate() = -((degree-30)*0.6)/100) when their act() takes a second argument.
     gamemode None | "ice" | "temper" (tron/game.py:163-178); spawns follow make_game(mode=spawn_mode).
     -> dict(p1_wins, p2_wins, draws, games, mean_ticks, p1_win_rating)   (p1_win_rating = p1/(p1+p2), play.py:94)
     """
     model2 = model2 or model1
     env = BatchedTron(n_games, width, height, device=device, obs_dtype=obs_dtype, obs_enc=obs_enc, auto_reset=False, seed=seed,
-                      slide_mode=gamemode, slide_rate=slide, spawn_mode=spawn_mode, collect_stats=True)
-    if gamemode == "temper":  # per-game degree / weights like Game.__init__ (game.py:83,87)
-        g = torch.Generator(device="cpu").manual_seed(seed)
-        env.slide_params[:, 0] = torch.randint(-30, 31, (n_games,), generator=g).to(torch.int8)
-        env.slide_params[:, 1] = torch.randint(40, 102, (n_games,), generator=g).to(torch.int8)
-        env.slide_params[:, 2] = torch.randint(40, 102, (n_games,), generator=g).to(torch.int8)
-    obs = env.reset()
+                      slide_mode=gamemode, slide_rate=slide, spawn_mode=spawn_mode, collect_stats=True, layout=layout, game_params=True)
+    obs = env.reset()  # draws every game's degree / weights like Game.__init__ (game.py:83,87)
     act = torch.empty((n_games, 2), dtype=torch.uint8, device=env.device)
     limit = max_ticks or (width * height + 2)
+    rate = (-((env.slide_params[:, 0].float() - 30) * 0.6) / 100).unsqueeze(1)  # Game.get_rate() (game.py:96-100); games never reset here
 
     def choose(m, o, player):
         if isinstance(m, str) and m == "minimax":  # the reference's scripted opponent, MinimaxPlayer(2, "voronoi")
             return env.minimax_actions(player)
-        a = m.act(o) if hasattr(m, "act") else m(o)
+        fn = m.act if hasattr(m, "act") else m
+        if _takes_extra(fn):
+            a = fn(o, env.extra[:, 0] if player == 1 else rate)
+        else:
+            a = fn(o)
         return torch.as_tensor(a, device=env.device).reshape(-1).to(torch.uint8)
 
     ticks = 0

@@ -186,7 +186,9 @@ typedef struct tron_step_args {
     int32_t slide_mode;   /* TRON_SLIDE_* */
     float slide_rate;     /* TRON_SLIDE_ICE */
     const uint8_t* slide_tape;  /* device [N,2] for TRON_SLIDE_TAPE */
-    int8_t* slide_params;       /* device [N,4] {degree, weight1, weight2, 0} for TRON_SLIDE_TEMPER; re-drawn on auto-reset */
+    int8_t* slide_params;       /* device [N,4] {degree, weight1, weight2, 0}: the per-game parameters Game.__init__ draws for every
+                                   game in every mode (tron/game.py:83,87).  Whenever given they are re-drawn for each game that is
+                                   reset (tron_reset_ex, auto-reset); TRON_SLIDE_TEMPER needs them (slip rate), `extra` reports them. */
 
     uint64_t* stats;      /* device [TRON_STATS_SLOTS*TRON_STATS_FIELDS] or NULL */
 
@@ -241,9 +243,9 @@ int tron_build_plane_tables(const int8_t lut6[6], int obs_enc, int8_t* tab /* [2
 int tron_reset(void* state, int n_envs, int width, int height, int layout, const int8_t* spawn, int spawn_mode,
                const uint8_t* env_mask, uint64_t seed, uint64_t counter, uint64_t env_id_base,
                tron_stream_t stream);
-/* tron_reset with the full argument block: additionally draws the per-game temper parameters (slide_mode TRON_SLIDE_TEMPER:
- * slide_params[N,4] = {degree, weight1, weight2, 0}, Game.__init__ tron/game.py:83,87) for every env it resets and fills
- * `extra`.  Uses state, geometry, layout, spawn, spawn_mode, seed, counter, env_id_base, slide_mode, slide_params, extra. */
+/* tron_reset with the full argument block: additionally draws the per-game parameters (slide_params[N,4] = {degree, weight1,
+ * weight2, 0}, Game.__init__ tron/game.py:83,87) for every env it resets when slide_params is given, and fills `extra`.
+ * Uses state, geometry, layout, spawn, spawn_mode, seed, counter, env_id_base, slide_mode, slide_params, extra. */
 int tron_reset_ex(const tron_step_args* args, const uint8_t* env_mask, tron_stream_t stream);
 /* One tick of every env, fused with observation encoding, rewards, done/winner and auto-reset. */
 int tron_step(const tron_step_args* args, tron_stream_t stream);

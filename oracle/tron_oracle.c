@@ -136,7 +136,7 @@ int oracle_reset_ex(const tron_step_args* a, const uint8_t* mask) {
             const uint64_t env = a->env_id_base + (uint64_t)e;
             if (a->spawn) memcpy(s, a->spawn + 4 * (size_t)e, 4); else rng_spawn(a->seed, a->counter, env, W, H, a->spawn_mode, s);
             fresh_game(grid + (size_t)e * C, meta + e, W, H, s);
-            if (a->slide_mode == TRON_SLIDE_TEMPER && a->slide_params) rng_temper(a->seed, a->counter, env, a->slide_params + 4 * (size_t)e);
+            if (a->slide_params) rng_temper(a->seed, a->counter, env, a->slide_params + 4 * (size_t)e);
         }
         write_extra(a, e);
     }
@@ -310,7 +310,7 @@ static void step_tick(const tron_step_args* a, uint64_t counter, const void* act
                     int8_t s[4];
                     if (spawn) memcpy(s, spawn + 4 * (size_t)e, 4); else rng_spawn(a->seed, counter, env, W, H, a->spawn_mode, s);
                     fresh_game(g, m, W, H, s);
-                    if (a->slide_mode == TRON_SLIDE_TEMPER && a->slide_params) rng_temper(a->seed, counter, env, (int8_t*)a->slide_params + 4 * (size_t)e);
+                    if (a->slide_params) rng_temper(a->seed, counter, env, (int8_t*)a->slide_params + 4 * (size_t)e);
                 }
             }
         }

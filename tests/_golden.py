@@ -63,3 +63,25 @@ def digest_with(env_factory, seed, ngames, W=10):
             h.update(bytes([int(done), int(wn[0])]))
         wins[int(wn[0])] += 1
     return h.hexdigest(), steps, wins
+
+
+# ---- learn-step fixture (tests/golden/learn.npz, made by make_learn_golden.py from the reference's own learn steps) ----
+def fill_params(net, seed):
+    """Deterministic, framework-independent initial weights: every parameter of `net` (in named_parameters order) is drawn from
+    numpy's PCG64 as uniform(-1/sqrt(fan_in), 1/sqrt(fan_in)) (the scale of PyTorch's default Conv2d / Linear init).  Used by the
+    fixture generator on the reference's nets and by the tests on ours, so the fixture does not have to store 2 MB per net."""
+    import torch
+    rng = np.random.default_rng(seed)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            w = dict(net.named_parameters())[name.rsplit(".", 1)[0] + ".weight"]
+            fan_in = int(np.prod(w.shape[1:]))
+            b = 1.0 / np.sqrt(fan_in)
+            p.copy_(torch.from_numpy(rng.uniform(-b, b, size=tuple(p.shape)).astype(np.float32)))
+
+
+def summarize(t):
+    """compact signature of a tensor: [sum, sum of |x|] in float64 and up to 256 evenly strided elements"""
+    a = np.asarray(t, dtype=np.float32).reshape(-1)
+    stride = max(1, a.size // 256)
+    return np.array([a.astype(np.float64).sum(), np.abs(a.astype(np.float64)).sum()]), a[::stride][:256].copy()

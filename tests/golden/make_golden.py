@@ -40,8 +40,15 @@ def import_reference():
                 "    def __getitem__(self, i): return list(self.keys())[i]\n")
     for m in [k for k in sys.modules if k.split(".")[0] in ("tron", "config", "DQN", "DDQN", "Net")]:
         del sys.modules[m]  # never mix the reference's modules with the drop-in mirrors of the same names
+    # the reference's tron/ has no __init__.py (namespace package): a regular package of the same name ANYWHERE on sys.path would
+    # win, so the drop-in mirror's directory must not be importable while the reference is
+    sys.path[:] = [p for p in sys.path if os.path.basename(os.path.normpath(p or ".")) != "deep-q-learning_tron_b200"]
     sys.path.insert(0, shim)
     sys.path.insert(0, REF)
+    try:  # tron.game imports torchvision; import it BEFORE the file-less namespace module `tron` exists (torchvision's op registration
+        import torchvision  # noqa: F401  walks sys.modules with inspect.getmodule, which raises on namespace packages)
+    except Exception:
+        pass
     import tron.game as game  # noqa
     import tron.util as util  # noqa
     import tron.player as player  # noqa

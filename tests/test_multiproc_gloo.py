@@ -29,7 +29,29 @@ def _worker(rank, world, port, q):
     dist.all_gather(gathered, torch.cat([g.reshape(-1) for g in local]))
     want = torch.stack(gathered).mean(0)
     got = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
-    q.put((rank, bool(torch.allclose(got, want, atol=1e-6)), env_shard(1000003)))
+    ok = bool(torch.allclose(got, want, atol=1e-6))
+    # the Agent keeps every gradient in one flat buffer (parameters' .grad are views): one all-reduce, no packing
+    torch.manual_seed(1)
+    agent = DDQN.Agent(in_planes=3, device="cpu", frame_dtype=torch.float32, data_parallel=True)
+    g = torch.Generator().manual_seed(10 + rank)
+    exp = (torch.randn(8, 3, 12, 12, generator=g), torch.randint(0, 4, (8, 1), generator=g), torch.randn(8, 1, generator=g),
+           torch.randn(8, 3, 12, 12, generator=g), torch.zeros(8, 1))
+    agent.qnetwork_local.dropout.p = 0.0
+    w0 = [p.detach().clone() for p in agent.qnetwork_local.parameters()]
+    agent._backward(exp, DDQN.GAMMA)
+    mine = agent.flat_grad.clone()
+    assert all(p.grad.data_ptr() >= agent.flat_grad.data_ptr() for p in agent.qnetwork_local.parameters())
+    DDQN.allreduce_gradients(agent.qnetwork_local, agent.flat_grad)
+    both = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    ok = ok and bool(torch.allclose(agent.flat_grad, torch.stack(both).mean(0), atol=1e-6)) and float(mine.abs().sum()) > 0
+    ok = ok and bool(torch.allclose(torch.cat([p.grad.reshape(-1) for p in agent.qnetwork_local.parameters()]), agent.flat_grad))
+    agent._apply()  # identical averaged gradients + identical initial weights (broadcast) -> identical weights on both ranks
+    w1 = torch.cat([p.detach().reshape(-1) for p in agent.qnetwork_local.parameters()])
+    ws = [torch.zeros_like(w1) for _ in range(world)]
+    dist.all_gather(ws, w1)
+    ok = ok and bool(torch.equal(ws[0], ws[1])) and not bool(torch.equal(w1, torch.cat([w.reshape(-1) for w in w0])))
+    q.put((rank, ok, env_shard(1000003)))
     dist.barrier()
     dist.destroy_process_group()
 

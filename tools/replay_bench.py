@@ -43,8 +43,12 @@ def main():
             t = timed(lambda: ring.gather(idx, torch.float32), 20)
             Bg = k * (2 * F * es + 2 * F * 4 + 30)
             print(json.dumps(dict(op="replay_gather->f32", frame=name, rows=k, seconds=t, rows_per_s=k / t, GBps=Bg / t / 1e9, frac_of_measured_peak=Bg / t / 1e9 / PEAK)))
-        t = timed(lambda: ring.sample_indices(64), 50)
-        print(json.dumps(dict(op="replay_sample_indices k=64", seconds=t)))
+        for k in (64, 4096, 262144):
+            t = timed(lambda: ring.sample_indices(k), 50)
+            print(json.dumps(dict(op="replay_sample_indices", k=k, seconds=t)))
+            t = timed(lambda: ring.sample(k), 50)
+            Bg = k * (2 * F * es + 2 * F * 4 + 30)
+            print(json.dumps(dict(op="replay_sample_gather->f32 (one launch)", frame=name, k=k, seconds=t, GBps=Bg / t / 1e9, frac_of_measured_peak=Bg / t / 1e9 / PEAK)))
         del ring, s, s2
         torch.cuda.empty_cache()
 

@@ -262,6 +262,7 @@ def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloa
     else:
         obs = env.reset() if not resume else env.observe()
     events = []
+    n_learn = 0
     last_stats = env.stats_dict()
     batch = agent.memory.batch_size
     for t in range(start_tick, start_tick + env_steps):
@@ -284,6 +285,7 @@ def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloa
         have = len(frames) if frames is not None else len(agent.memory)
         if (t + 1) % learn_every == 0 and have > batch:
             exp = frames.sample(batch) if frames is not None else agent.memory.sample()
+            n_learn += 1
             if overlap:
                 agent.learn_begin(exp)
             else:
@@ -315,5 +317,5 @@ def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloa
         timings.update(ticks=len(events), q_forward_ms=sum(e[0].elapsed_time(e[1]) for e in events),
                        env_replay_ms=sum(e[1].elapsed_time(e[2]) for e in events), learn_ms=sum(e[2].elapsed_time(e[3]) for e in events),
                        allreduce_ms=sum(a.elapsed_time(b) for a, b in agent.allreduce_events), allreduce_calls=len(agent.allreduce_events),
-                       learn_steps=agent.steps, replay=replay, layout=env.layout)
+                       learn_steps=n_learn, replay=replay, layout=env.layout)
     return agent, env

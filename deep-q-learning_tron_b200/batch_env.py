@@ -25,8 +25,8 @@ def auto_layout(width, height, obs_enc, slide_mode):
     no_slide = slide_mode in (None, abi.SLIDE_NONE)
     if width == 10 and height == 10 and no_slide:
         return "bits10"
-    if width * height <= 128:
-        return "bits"
+    if width == 10 and height == 10:
+        return "bits"   # config.py's board with a slide mode (GAME_MODE="temper"): three bit planes
     if enc_none and (width + 2) * (height + 2) >= 1024:
         return "trail"
     return "tile8"

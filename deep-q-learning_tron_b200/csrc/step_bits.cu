@@ -11,9 +11,10 @@
 // trip.  For the observation the owning thread expands its planes into an int8 Tile.value tile in shared memory (10x10: one
 // funnel-shift + bit-spread multiply per 4 cells) and the CTA runs the PRMT encode with 16-byte streaming stores.
 // HBM traffic per game-tick: state read + written (32 or 48 B each way) + observation planes + ~28 B metadata.
-//
-// PERSIST variant: a CTA walks over several tiles and loads the next tile's planes / metadata / actions into registers before it
-// encodes the current one, so the load latency at the head of a tile hides behind the previous tile's store phase.
+// Measured on B200 (profiles/r2_sweep.jsonl): the LINEAR store schedule below takes the 10x10 kernels from 0.94-0.97 to 0.98 of
+// the measured HBM peak (pop_up 3 planes 0.95 -> 0.98, + const plane 0.94 -> 0.99); a persistent-CTA variant with register
+// prefetch of the next tile was tried and dropped (0.80: it serialises the tick and store phases that otherwise overlap
+// across the CTAs resident on an SM).
 #include "launch.h"
 #include "step_kernels.cuh"
 
@@ -198,7 +199,7 @@ __device__ __forceinline__ void encode_tile_linear144(const int8_t* tile, int nG
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-template <bool SLIDE, int W_T, int OD, int LP, bool CP, int CH, int MODE, bool PERSIST>
+template <bool SLIDE, int W_T, int OD, int LP, bool CP, int CH, int MODE>
 __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = W_T ? (W_T + 2) * (W_T + 2) : p.C;
@@ -206,51 +207,34 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
     uint8_t* tflag = (uint8_t*)(tile + ((p.G * C + 15) & ~15));  // [G] "this game just finished" (terminal-frame pass)
     PlaneTab* smtab = (PlaneTab*)(tflag + ((p.G + 15) & ~15));   // [2][3] tables for the linear schedule
     const int tid = threadIdx.x;
-    const bool linear = W_T == 10 && (p.variant & 2);
+    // store schedule: linear (one contiguous 512-byte run per warp store) for the two-plane 10x10 kernels; the slide kernels
+    // spend more issue slots in the tick and are faster with the per-plane schedule.  TRON_OPT_ENCODE_VARIANT 2 / 8 force one.
+    const bool linear = W_T == 10 && ((p.variant & 2) || (!SLIDE && !(p.variant & 8)));
     if (LP > 0 && linear) {
         if (tid < 6) smtab[tid] = p.tab[tid / 3][tid % 3];
         __syncthreads();
     }
-    const long long n_tiles = ((long long)p.N + p.G - 1) / p.G;
     using Cells = BitCells<SLIDE, W_T>;
-
-    PlaneRegs<SLIDE> pre_pl;
-    uint2 pre_meta = make_uint2(0, 0);
-    int pre_act[2] = {255, 255};
-    const bool fetch_planes = !(MODE == MODE_RESET && p.env_mask == nullptr);
-    const bool pre_actions = PERSIST && MODE == MODE_STEP && p.actions != nullptr && p.T == 1;
-    auto fetch = [&](long long tl) {
-        const long long env = tl * p.G + tid;
-        if (tid < p.G && env < p.N) {
-            if (fetch_planes) pre_pl = load_planes<SLIDE>(p, env);
-            pre_meta = p.meta[env];
-            if (pre_actions) { pre_act[0] = read_action(p.actions, p.action_dtype, 2 * (size_t)env); pre_act[1] = read_action(p.actions, p.action_dtype, 2 * (size_t)env + 1); }
+    const long long env0 = (long long)blockIdx.x * p.G;
+    const int nG = (int)min((long long)p.G, (long long)p.N - env0);
+    const bool owner = tid < nG;
+    const long long env = env0 + tid;
+    Cells g;
+    g.clear(); g.Wr = p.W; g.Hr = p.H;
+    EnvState e = unpack_meta(make_uint2(0, 0));
+    if (owner) {
+        if (!(MODE == MODE_RESET && p.env_mask == nullptr)) set_planes(g, load_planes<SLIDE>(p, env));
+        e = unpack_meta(p.meta[env]);
+    }
+    const int T = MODE == MODE_STEP ? p.T : 1;
+    for (int t = 0; t < T; ++t) {
+        bool fin = false;
+        if (MODE != MODE_OBSERVE && owner) {
+            BoxRegs bx;
+            fin = env_tick<MODE, false>(g, p, e, env, t, tid, bx);
         }
-    };
-    pre_pl.a = pre_pl.b = pre_pl.c = make_ulonglong2(0ull, 0ull);
-    if (blockIdx.x < n_tiles) fetch(blockIdx.x);
-
-    for (long long tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
-        const long long env0 = tl * p.G;
-        const int nG = (int)min((long long)p.G, (long long)p.N - env0);
-        const bool owner = tid < nG;
-        const long long env = env0 + tid;
-        Cells g;
-        g.clear(); g.Wr = p.W; g.Hr = p.H;
-        set_planes(g, pre_pl);
-        if (!fetch_planes) g.clear();
-        EnvState e = unpack_meta(pre_meta);
-        int act_now[2] = {pre_act[0], pre_act[1]};
-        if (PERSIST && tl + gridDim.x < n_tiles) fetch(tl + gridDim.x);  // next tile's state is in flight while this one is encoded
-
-        const int T = MODE == MODE_STEP ? p.T : 1;
-        for (int t = 0; t < T; ++t) {
-            bool fin = false;
-            if (MODE != MODE_OBSERVE && owner) {
-                BoxRegs bx;
-                fin = env_tick<MODE, false>(g, p, e, env, t, tid, bx, pre_actions ? act_now : nullptr);
-            }
-            if (LP > 0 && MODE == MODE_STEP && p.obs_term) {  // last frame of the games that just finished (-> obs_terminal)
+        if constexpr (LP > 0 && MODE == MODE_STEP) {
+            if (p.obs_term) {  // last frame of the games that just finished (-> obs_terminal)
                 if (owner) {
                     tflag[tid] = fin ? 1 : 0;
                     if (fin) expand_tile<SLIDE, W_T, false>(g, e.tr1, e.tc1, e.tr2, e.tc2, tile + tid * C);
@@ -261,21 +245,23 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
                 else encode_tile<(W_T == 10 ? 144 : 0), kBitsThreads, OD, LP, CP, CH>(tile, nG, env0, p, tt, p.obs_term, tflag);
                 __syncthreads();
             }
-            if (fin) g.clear();
-            if (MODE == MODE_OBSERVE && owner) emit_extra(p, env);
-            if (LP > 0 && (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1)) {
+        }
+        if (fin) g.clear();
+        if (MODE == MODE_OBSERVE && owner) emit_extra(p, env);
+        if constexpr (LP > 0) {
+            if (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1) {
                 if (owner) expand_tile<SLIDE, W_T, false>(g, e.r1, e.c1, e.r2, e.c2, tile + tid * C);
                 __syncthreads();
                 const int tt = (MODE == MODE_STEP && p.obs_every_tick) ? t : 0;
                 if (linear) encode_tile_linear144<OD, LP, CP>(tile, nG, env0, p, tt, smtab);
                 else encode_tile<(W_T == 10 ? 144 : 0), kBitsThreads, OD, LP, CP, CH>(tile, nG, env0, p, tt);
-                if (T > 1 || PERSIST) __syncthreads();  // the tile is rewritten by the next tick / the next tile
+                if (T > 1) __syncthreads();  // the tile is rewritten by the next tick
             }
         }
-        if (MODE != MODE_OBSERVE && owner) {
-            store_planes(p, env, g);
-            p.meta[env] = pack_meta(e);
-        }
+    }
+    if (MODE != MODE_OBSERVE && owner) {
+        store_planes(p, env, g);
+        p.meta[env] = pack_meta(e);
     }
 }
 
@@ -289,19 +275,9 @@ template <bool SLIDE, int W_T, int OD, int LP, bool CP, int CH, int MODE>
 static int launch_bits_one(const StepParams& p, cudaStream_t s) {
     const long long n_tiles = ((long long)p.N + p.G - 1) / p.G;
     const size_t smem = bits_smem(p.G, p.C, LP);
-    const bool persist = MODE == MODE_STEP && (p.variant & 1);
-    if (persist) {
-        auto kern = step_bits_kernel<SLIDE, W_T, OD, LP, CP, CH, MODE, true>;
-        if (smem > 48 * 1024 && ensure_dynamic_smem((const void*)kern, smem) != TRON_OK) return TRON_ERR_CUDA;
-        int per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBitsThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        const long long cap = (long long)sm_count() * per_sm;
-        kern<<<(unsigned)(n_tiles < cap ? n_tiles : cap), kBitsThreads, smem, s>>>(p);
-    } else {
-        auto kern = step_bits_kernel<SLIDE, W_T, OD, LP, CP, CH, MODE, false>;
-        if (smem > 48 * 1024 && ensure_dynamic_smem((const void*)kern, smem) != TRON_OK) return TRON_ERR_CUDA;
-        kern<<<(unsigned)n_tiles, kBitsThreads, smem, s>>>(p);
-    }
+    auto kern = step_bits_kernel<SLIDE, W_T, OD, LP, CP, CH, MODE>;
+    if (smem > 48 * 1024 && ensure_dynamic_smem((const void*)kern, smem) != TRON_OK) return TRON_ERR_CUDA;
+    kern<<<(unsigned)n_tiles, kBitsThreads, smem, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 template <bool SLIDE, int W_T, int OD, int CH, int MODE>

@@ -37,6 +37,25 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+class _OnDevice:
+    """`with _OnDevice(dev):` -- like torch.cuda.device(dev) but free when `dev` already is the current device (the common case;
+    the torch context manager costs ~4 us per call, more than a small tick kernel)."""
+    __slots__ = ("dev", "ctx")
+
+    def __init__(self, dev):
+        self.dev, self.ctx = dev, None
+
+    def __enter__(self):
+        if torch.cuda.current_device() != self.dev.index:
+            self.ctx = torch.cuda.device(self.dev)
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+            self.ctx = None
+
+
 class StepResult(tuple):
     """(obs, reward, done, winner, ep_len) with attribute access."""
     __slots__ = ()
@@ -89,11 +108,12 @@ class BatchedTron:
         self.seed, self.env_id_base = int(seed), int(env_id_base)
         self.slide_mode = _SLIDE_OF[slide_mode] if (slide_mode is None or isinstance(slide_mode, str)) else int(slide_mode)
         self.slide_rate = float(slide_rate)
+        self._tmpl = self._tmpl_key = None
         self.counter = 0
         self.counter_dev = None  # device u64; set by use_device_counter() so captured CUDA graphs advance the RNG between replays
         nbytes = C.c_size_t()
         _lib.check(self.lib.tron_state_bytes(self.N, self.W, self.H, self.layout, C.byref(nbytes)), "tron_state_bytes")
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             self.state = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)
             self.stats = torch.zeros(abi.STATS_SLOTS * abi.STATS_FIELDS, dtype=torch.int64, device=self.device) if collect_stats else None
             if game_params is None:
@@ -135,12 +155,17 @@ class BatchedTron:
             _lib.check(self.lib.tron_advance_counter(self.counter_dev.data_ptr(), n, self._stream()), "tron_advance_counter")
 
     def _args(self, **kw):
-        a = abi.new_step_args(n_envs=self.N, width=self.W, height=self.H, layout=self.layout, state=self.state.data_ptr(),
-                              obs_dtype=self.obs_dtype, obs_enc=self.obs_enc, lut=self.lut, const_plane=self.const_plane,
-                              reward_table=self.reward_table, auto_reset=int(self.auto_reset), seed=self.seed,
-                              env_id_base=self.env_id_base, slide_mode=self.slide_mode, slide_rate=self.slide_rate, spawn_mode=self.spawn_mode,
-                              policy=self.policy, policy_epsilon=self.policy_epsilon,
-                              slide_params=_ptr(self.slide_params), stats=_ptr(self.stats), extra=_ptr(self.extra))
+        """argument block of one call: a copy of the per-environment template with the per-call fields filled in"""
+        key = (self.policy, self.policy_epsilon, self.auto_reset, self.slide_rate, self.seed, self.env_id_base)
+        if self._tmpl is None or self._tmpl_key != key:
+            self._tmpl = abi.new_step_args(n_envs=self.N, width=self.W, height=self.H, layout=self.layout, state=self.state.data_ptr(),
+                                           obs_dtype=self.obs_dtype, obs_enc=self.obs_enc, lut=self.lut, const_plane=self.const_plane,
+                                           reward_table=self.reward_table, auto_reset=int(self.auto_reset), seed=self.seed,
+                                           env_id_base=self.env_id_base, slide_mode=self.slide_mode, slide_rate=self.slide_rate, spawn_mode=self.spawn_mode,
+                                           policy=self.policy, policy_epsilon=self.policy_epsilon,
+                                           slide_params=_ptr(self.slide_params), stats=_ptr(self.stats), extra=_ptr(self.extra))
+            self._tmpl_key = key
+        a = abi.StepArgs.from_buffer_copy(self._tmpl)
         for k, v in kw.items():
             setattr(a, k, v)
         return a
@@ -178,7 +203,7 @@ class BatchedTron:
         sp = self._dev(spawn, torch.int8, (self.N, 4), "spawn")
         mk = self._dev(mask, torch.uint8, (self.N,), "mask")
         a = self._args(spawn=_ptr(sp), counter=counter, obs_enc=abi.ENC_NONE)
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.tron_reset_ex(C.byref(a), _ptr(mk), self._stream()), "tron_reset_ex")
         return self.observe(obs) if self.P else None
 
@@ -189,7 +214,7 @@ class BatchedTron:
             obs = self.new_obs()
         self._out(obs, (self.N, 2, self.P, self.W + 2, self.H + 2), _TORCH_OF[self.obs_dtype], "obs")
         a = self._args(obs=obs.data_ptr())
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.tron_observe(C.byref(a), self._stream()), "tron_observe")
         return obs
 
@@ -231,7 +256,7 @@ class BatchedTron:
         a = self._args(actions=_ptr(actions), action_dtype=0 if actions is None else _CODE_OF[actions.dtype], obs=_ptr(obs),
                        reward=reward.data_ptr(), done=done.data_ptr(), winner=winner.data_ptr(), ep_len_out=_ptr(ep_len),
                        spawn=_ptr(sp), slide_tape=_ptr(sl), counter=counter, counter_dev=cdev, obs_terminal=_ptr(obs_terminal))
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             _lib.check(self.lib.tron_step(C.byref(a), self._stream()), "tron_step")
             self._advance(adv)
         return StepResult((obs, reward, done, winner, ep_len))
@@ -258,7 +283,7 @@ class BatchedTron:
         a = self._args(actions=_ptr(act), action_dtype=0 if act is None else _CODE_OF[act.dtype], obs=_ptr(obs),
                        reward=reward.data_ptr(), done=done.data_ptr(), winner=winner.data_ptr(), ep_len_out=ep_len.data_ptr(),
                        spawn=_ptr(sp), counter=counter, counter_dev=cdev, n_ticks=T, obs_every_tick=int(obs_every_tick))
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             _lib.check(self.lib.tron_step_many(C.byref(a), self._stream()), "tron_step_many")
             self._advance(adv)
         return StepResult((obs, reward, done, winner, ep_len))
@@ -270,7 +295,7 @@ class BatchedTron:
                    heads=torch.empty((N, 4), dtype=torch.int8, device=dev), alive=torch.empty((N, 2), dtype=torch.uint8, device=dev),
                    done=torch.empty(N, dtype=torch.uint8, device=dev), winner=torch.empty(N, dtype=torch.uint8, device=dev),
                    ep_len=torch.empty(N, dtype=torch.int32, device=dev))
-        with torch.cuda.device(dev):
+        with _OnDevice(dev):
             _lib.check(self.lib.tron_export_grid(self.state.data_ptr(), N, self.W, self.H, self.layout, out["tiles"].data_ptr(),
                                                  out["heads"].data_ptr(), out["alive"].data_ptr(), out["done"].data_ptr(),
                                                  out["winner"].data_ptr(), out["ep_len"].data_ptr(), self._stream()), "tron_export_grid")
@@ -281,7 +306,7 @@ class BatchedTron:
         t = self._dev(tiles, torch.int8, (N, self.W + 2, self.H + 2), "tiles"); h = self._dev(heads, torch.int8, (N, 4), "heads")
         al = self._dev(alive, torch.uint8, (N, 2), "alive"); d = self._dev(done, torch.uint8, (N,), "done")
         w = self._dev(winner, torch.uint8, (N,), "winner"); k = self._dev(ep_len, torch.int32, (N,), "ep_len")
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.tron_import_grid(self.state.data_ptr(), self.N, self.W, self.H, self.layout, _ptr(t), _ptr(h),
                                                  _ptr(al), _ptr(d), _ptr(w), _ptr(k), self._stream()), "tron_import_grid")
 
@@ -292,7 +317,7 @@ class BatchedTron:
         cdev = None
         if counter is None:
             counter, cdev = (0, self.counter_dev.data_ptr()) if self.counter_dev is not None else (self.counter, None)
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.tron_random_actions(out.data_ptr(), self.N, self.seed, counter, cdev, self.env_id_base, self._stream()),
                        "tron_random_actions")
         return out
@@ -310,7 +335,7 @@ class BatchedTron:
         cdev = None
         if counter is None:
             counter, cdev = (0, self.counter_dev.data_ptr()) if self.counter_dev is not None else (self.counter, None)
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.tron_select_actions(q2.data_ptr(), _CODE_OF[q2.dtype], q2.shape[0], float(epsilon), out.data_ptr(),
                                                     self.seed, counter, cdev, 2 * self.env_id_base, self._stream()), "tron_select_actions")
         return out.view(-1, 2) if out.numel() == 2 * self.N else out
@@ -325,7 +350,7 @@ class BatchedTron:
         cdev = None
         if counter is None:
             counter, cdev = (0, self.counter_dev.data_ptr()) if self.counter_dev is not None else (self.counter, None)
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.tron_minimax_actions(tiles.data_ptr(), self.N, self.W, self.H, int(player), int(tie_mode), self.seed, counter, cdev,
                                                      self.env_id_base, out.data_ptr(), _ptr(vals), self._stream()), "tron_minimax_actions")
         return (out, vals) if want_values else out

@@ -13,7 +13,7 @@ import torch
 
 from . import _abi as abi
 from . import _lib
-from .batch_env import _CODE_OF, _TORCH_OF
+from .batch_env import _CODE_OF, _TORCH_OF, _OnDevice
 
 
 class ReplayRing:
@@ -68,7 +68,7 @@ class ReplayRing:
         while off < n:  # the ABI takes at most `capacity` transitions per call
             m = min(chunk, n - off)
             fo = off * self.F
-            with torch.cuda.device(self.device):
+            with _OnDevice(self.device):
                 _lib.check(self.lib.replay_push(C.byref(self.ring), self.cursor, state.view(-1)[fo:].data_ptr(),
                                                 next_state.view(-1)[fo:].data_ptr(), action[off:].data_ptr(), reward.view(-1)[off:].data_ptr(),
                                                 done[(off // done_stride):].data_ptr(), done_stride, m, self._stream()), "replay_push")
@@ -81,7 +81,7 @@ class ReplayRing:
         if not 0 < k <= len(self):
             raise ValueError("sample_indices: need 0 < k <= len(ring)=%d, got %d" % (len(self), k))
         idx = torch.empty(k, dtype=torch.int64, device=self.device)
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.replay_sample_indices(len(self), k, self.seed, counter, idx.data_ptr(), self._stream()),
                        "replay_sample_indices")
         return idx
@@ -97,7 +97,7 @@ class ReplayRing:
         a = torch.empty((k, 1), dtype=torch.int64, device=self.device)
         r = torch.empty((k, 1), dtype=torch.float32, device=self.device)
         d = torch.empty((k, 1), dtype=torch.float32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.replay_gather(C.byref(self.ring), idx.data_ptr(), k, s.data_ptr(), s2.data_ptr(), _CODE_OF[out_dtype],
                                               a.data_ptr(), r.data_ptr(), d.data_ptr(), self._stream()), "replay_gather")
         return s, a, r, s2, d
@@ -117,7 +117,7 @@ class ReplayRing:
             raise ValueError("sample: need 0 < k <= len(ring)=%d, got %d" % (len(self), k))
         s, a, r, s2, d = self._outputs(k, out_dtype)
         idx = torch.empty(k, dtype=torch.int64, device=self.device) if want_indices else None
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.replay_sample_gather(C.byref(self.ring), len(self), k, self.seed, counter, s.data_ptr(), s2.data_ptr(),
                                                      _CODE_OF[out_dtype], a.data_ptr(), r.data_ptr(), d.data_ptr(),
                                                      None if idx is None else idx.data_ptr(), self._stream()), "replay_sample_gather")
@@ -204,7 +204,7 @@ class FrameRing:
         r = torch.empty((k, 1), dtype=torch.float32, device=self.device)
         d = torch.empty((k, 1), dtype=torch.float32, device=self.device)
         idx = torch.empty(k, dtype=torch.int64, device=self.device) if want_indices else None
-        with torch.cuda.device(self.device):
+        with _OnDevice(self.device):
             _lib.check(self.lib.replay_frames_sample_gather(C.byref(self.fr), self.tick - n_ticks, n_ticks, k, self.seed, counter, s.data_ptr(),
                                                             s2.data_ptr(), _CODE_OF[out_dtype], a.data_ptr(), r.data_ptr(), d.data_ptr(),
                                                             None if idx is None else idx.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),

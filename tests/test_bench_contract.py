@@ -58,4 +58,4 @@ def test_our_arm_config_legs():
     assert c["cfg5"]["value"] > 1e9 and c["cfg5"]["roofline"]["bound"] == "hbm" and 0 < c["cfg5"]["reset_fraction"] < 1
     for k in ("cfg3", "cfg4"):
         assert c[k]["value"] > 1e5 and set(c[k]["ms"]) >= {"q_forward", "env_replay", "learn"} and 0 < c[k]["env_replay_fraction_of_loop"] < 1
-    assert "allreduce" in c["cfg4"]["ms"] and c["cfg4"]["learn_steps"] == 10
+    assert "allreduce" in c["cfg4"]["ms"] and c["cfg4"]["learn_steps"] == 12

@@ -1,0 +1,11 @@
+set -x
+prof() { # name skip cmd...
+  name=$1; skip=$2; shift 2
+  "$@" > gpurun_out/plain_$name.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:step_ -s $skip -c 2 -o gpurun_out/r2_$name "$@" > gpurun_out/ncu_$name.log 2>&1
+  echo "$name rc=$?"
+}
+prof trail64 3 python tools/profile_case.py 2097152 64 bf16 none 4 trail --actions rng
+prof bits_temper 4 python tools/profile_case.py 4194304 10 bf16 lut1 4 bits --slide temper --actions rng
+prof bits10_lut1 4 python tools/profile_case.py 4194304 10 bf16 lut1 4 bits10
+prof bits10_popup3 4 python tools/profile_case.py 2097152 10 bf16 popup3 4 bits10
+ls -la gpurun_out/*.ncu-rep

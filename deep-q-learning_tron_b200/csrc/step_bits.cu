@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
         bool fin = false;
         if (MODE != MODE_OBSERVE && owner) {
             BoxRegs bx;
-            fin = env_tick<MODE, false>(g, p, e, env, t, tid, bx);
+            fin = env_tick<MODE, false, (SLIDE ? FEAT_ALL : FEAT_EPS)>(g, p, e, env, t, tid, bx);  // BITS10 has no slide plane
         }
         if constexpr (LP > 0 && MODE == MODE_STEP) {
             if (p.obs_term) {  // last frame of the games that just finished (-> obs_terminal)

@@ -48,78 +48,106 @@ __host__ __device__ inline TrailStore trail_store(const StepParams& p) {
     return s;
 }
 
+// exact per-half "is zero" test of a 32-bit word holding two 16-bit entries: bit 15 / bit 31 of the result is set iff the
+// low / high half of x is zero (the top bit of each half is masked before the add, so no carry crosses the halves)
+__device__ __forceinline__ uint32_t zero_halves(uint32_t x) {
+    const uint32_t t = (x & 0x7FFF7FFFu) + 0x7FFF7FFFu;
+    return ~(t | x | 0x7FFF7FFFu);
+}
+
 struct TrailCells {
-    uint32_t hot[kTrailHot];  // list words 0..11
+    // list words 0..11 in registers.  Entries at positions >= n (stale leftovers of an earlier game) are overwritten with the
+    // impossible key 0xFFFF when the words are loaded, so that get() needs no validity test per entry.
+    uint32_t hot[kTrailHot];
     uint32_t* cold;           // this game's cold words (list words 12..)
-    int n[2];                 // entries per player at the start of the tick (those are in hot[] / cold[])
-    unsigned short fresh[4];  // entries appended during this tick (two bodies, up to two slide tiles)
-    int fresh_owner[4], n_fresh;
+    int n0, n1;               // entries per player at the start of the tick (those are in hot[] / cold[])
+    uint32_t fb, fs;          // entries appended during this tick: bodies {P1 | P2 << 16} and slide tiles, 0xFFFF = none
     int W, H;
     unsigned dirty;           // bit q: hot uint4 q changed
 
     __device__ __forceinline__ static unsigned short pack(int r, int c, bool slide) { return (unsigned short)((r & 0x7F) | (slide ? 0x80 : 0) | (c << 8)); }
 
+    __device__ __forceinline__ void start(int a, int b) { n0 = a; n1 = b; fb = fs = 0xFFFFFFFFu; dirty = 0; }
+    __device__ __forceinline__ void blank() {
+#pragma unroll
+        for (int w = 0; w < kTrailHot; ++w) hot[w] = 0xFFFFFFFFu;
+    }
+    __device__ __forceinline__ void clear() {  // fresh game: empty lists
+        n0 = n1 = 0; fb = fs = 0xFFFFFFFFu;
+        blank();
+    }
+    __device__ __forceinline__ void sanitize() {
+#pragma unroll
+        for (int w = 0; w < kTrailHot; ++w) hot[w] |= (w >= n0 ? 0x0000FFFFu : 0u) | (w >= n1 ? 0xFFFF0000u : 0u);
+    }
+
     __device__ __forceinline__ int get(int r, int c) const {
         if (r < 0 || c < 0 || r >= W || c >= H) return TRON_TILE_WALL;
-        const unsigned key = (unsigned)(r & 0x7F) | ((unsigned)c << 8);
-        bool hit = false;
+        const uint32_t key = (uint32_t)(r & 0x7F) | ((uint32_t)c << 8), key2 = key | (key << 16);
+        uint32_t hit = zero_halves((fb & 0xFF7FFF7Fu) ^ key2) | zero_halves((fs & 0xFF7FFF7Fu) ^ key2);
 #pragma unroll
-        for (int w = 0; w < kTrailHot; ++w) {  // word w = {entry (k=w, P1), entry (k=w, P2)}
-            const unsigned e1 = hot[w] & 0xFF7Fu, e2 = (hot[w] >> 16) & 0xFF7Fu;
-            hit |= (w < n[0] && e1 == key) | (w < n[1] && e2 == key);
-        }
-        const int nmax = max(n[0], n[1]);
+        for (int w = 0; w < kTrailHot; ++w) hit |= zero_halves((hot[w] & 0xFF7FFF7Fu) ^ key2);
+        const int nmax = max(n0, n1);
         for (int w = kTrailHot; w < nmax; ++w) {  // long episode: the rest of the lists, straight from memory
-            const uint32_t v = cold[w - kTrailHot];
-            hit |= (w < n[0] && (v & 0xFF7Fu) == key) | (w < n[1] && ((v >> 16) & 0xFF7Fu) == key);
+            const uint32_t z = zero_halves((cold[w - kTrailHot] & 0xFF7FFF7Fu) ^ key2);
+            hit |= z & ((w < n0 ? 0x00008000u : 0u) | (w < n1 ? 0x80000000u : 0u));
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hit |= (i < n_fresh && (fresh[i] & 0xFF7Fu) == key);
         return hit ? TRON_TILE_P1_BODY : TRON_TILE_EMPTY;  // callers only test for EMPTY
     }
     __device__ __forceinline__ void put(int r, int c, int tile) {
-        int owner;
-        bool slide = false;
-        if (tile == TRON_TILE_P1_BODY) owner = 0;
-        else if (tile == TRON_TILE_P2_BODY) owner = 1;
-        else if (tile == TRON_TILE_P1_SLIDE) { owner = 0; slide = true; }
-        else if (tile == TRON_TILE_P2_SLIDE) { owner = 1; slide = true; }
-        else return;  // heads are metadata
+        if (tile != TRON_TILE_P1_BODY && tile != TRON_TILE_P2_BODY && tile != TRON_TILE_P1_SLIDE && tile != TRON_TILE_P2_SLIDE) return;  // heads are metadata
         if (r < 0 || c < 0 || r >= W || c >= H) return;  // a head that left the board leaves no trail tile there
-        const unsigned short e = pack(r, c, slide);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (i == n_fresh) { fresh[i] = e; fresh_owner[i] = owner; }
-        n_fresh = min(n_fresh + 1, 4);
+        const bool slide = tile == TRON_TILE_P1_SLIDE || tile == TRON_TILE_P2_SLIDE;
+        const bool p2 = tile == TRON_TILE_P2_BODY || tile == TRON_TILE_P2_SLIDE;
+        const uint32_t e = pack(r, c, slide);
+        uint32_t& f = slide ? fs : fb;
+        f = p2 ? ((f & 0x0000FFFFu) | (e << 16)) : ((f & 0xFFFF0000u) | e);
     }
-    // append this tick's entries to the lists (registers for list words < 12, memory beyond)
-    __device__ __forceinline__ void commit() {
+    __device__ __forceinline__ void append(int owner, int k, uint32_t entry) {
+        if (!TRON_DCHECK(k < W * H, DBG_TRAIL_COUNT)) return;
+        const uint32_t v = entry << (16 * owner), keep = owner ? 0x0000FFFFu : 0xFFFF0000u;
+        if (k < kTrailHot) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (i >= n_fresh) continue;
-            const int o = fresh_owner[i], k = n[o];
-            if (!TRON_DCHECK(k < W * H, DBG_TRAIL_COUNT)) continue;
-            const uint32_t v = (uint32_t)fresh[i] << (16 * o), keep = o ? 0x0000FFFFu : 0xFFFF0000u;
-            if (k < kTrailHot) {
-#pragma unroll
-                for (int w = 0; w < kTrailHot; ++w)
-                    if (w == k) hot[w] = (hot[w] & keep) | v;
-                dirty |= 1u << (1 + (k >> 2));
-            } else {
-                ((unsigned short*)(cold + (k - kTrailHot)))[o] = fresh[i];
-            }
-            n[o] = k + 1;
+            for (int w = 0; w < kTrailHot; ++w)
+                if (w == k) hot[w] = (hot[w] & keep) | v;
+            dirty |= 1u << (1 + (k >> 2));
+        } else {
+            ((unsigned short*)(cold + (k - kTrailHot)))[owner] = (unsigned short)entry;
         }
-        n_fresh = 0;
+    }
+    // append this tick's entries to the lists (registers for list words < 12, memory beyond): per player the body, then the slide tile
+    __device__ __forceinline__ void commit() {
+        if (fs == 0xFFFFFFFFu && n0 == n1 && (fb & 0xFFFFu) != 0xFFFFu && (fb >> 16) != 0xFFFFu) {
+            // the common tick: both players leave one body, their lists are equally long -> the two entries are ONE list word
+            const int k = n0;
+            if (TRON_DCHECK(k < W * H, DBG_TRAIL_COUNT)) {
+                if (k < kTrailHot) {
+#pragma unroll
+                    for (int w = 0; w < kTrailHot; ++w)
+                        if (w == k) hot[w] = fb;
+                    dirty |= 1u << (1 + (k >> 2));
+                } else {
+                    cold[k - kTrailHot] = fb;
+                }
+            }
+            n0 = n1 = k + 1;
+        } else {
+            if ((fb & 0xFFFFu) != 0xFFFFu) append(0, n0++, fb & 0xFFFFu);
+            if ((fs & 0xFFFFu) != 0xFFFFu) append(0, n0++, fs & 0xFFFFu);
+            if ((fb >> 16) != 0xFFFFu) append(1, n1++, fb >> 16);
+            if ((fs >> 16) != 0xFFFFu) append(1, n1++, fs >> 16);
+        }
+        fb = fs = 0xFFFFFFFFu;
     }
     __device__ __forceinline__ void load_hot(const TrailStore& st, long long i, int upto_words) {
         // upto_words: list words that can hold valid entries (lazy variant) or kTrailHot
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
-            uint4 v = make_uint4(0, 0, 0, 0);
+            uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             if (4 * q < upto_words) v = st.hot[(long long)(1 + q) * st.SN + i];
             hot[4 * q] = v.x; hot[4 * q + 1] = v.y; hot[4 * q + 2] = v.z; hot[4 * q + 3] = v.w;
         }
+        sanitize();
     }
     __device__ __forceinline__ void store_dirty(const TrailStore& st, long long i) {
 #pragma unroll
@@ -129,7 +157,7 @@ struct TrailCells {
     }
 };
 
-template <int MODE>
+template <int MODE, int FEAT>
 __global__ void __launch_bounds__(kTrailThreads, 8) step_trail_kernel(const StepParams p) {
     const int tid = threadIdx.x;
     const long long env = (long long)blockIdx.x * kTrailThreads + tid;
@@ -139,23 +167,25 @@ __global__ void __launch_bounds__(kTrailThreads, 8) step_trail_kernel(const Step
     const uint4 hdr = st.hot[i];
     EnvState e = unpack_meta(make_uint2(hdr.x, hdr.y));
     TrailCells g;
-    g.W = p.W; g.H = p.H; g.cold = st.cold + i * st.cw; g.dirty = 0; g.n_fresh = 0;
-    g.n[0] = (int)(hdr.z & 0xFFFFu); g.n[1] = (int)(hdr.z >> 16);
+    g.W = p.W; g.H = p.H; g.cold = st.cold + i * st.cw;
+    g.start((int)(hdr.z & 0xFFFFu), (int)(hdr.z >> 16));
     if (MODE == MODE_STEP) {
         // lazy variant: a list word beyond max(n1,n2) holds nothing valid, and this tick appends at most two entries per player,
         // so only the uint4s up to word max(n)+1 are needed (second round trip only for games older than 2 ticks)
-        const int need = (p.variant & 4) ? min(kTrailHot, max(g.n[0], g.n[1]) + 2 * p.T) : kTrailHot;
+        const int need = (p.variant & 4) ? min(kTrailHot, max(g.n0, g.n1) + 2 * p.T) : kTrailHot;
         g.load_hot(st, i, need);
+    } else {
+        g.blank();  // MODE_RESET never looks at the lists; games that are not reset keep their counts
     }
     const int T = MODE == MODE_STEP ? p.T : 1;
     for (int t = 0; t < T; ++t) {
         BoxRegs bx;
-        const bool do_reset = env_tick<MODE, false>(g, p, e, env, t, tid, bx);
-        if (do_reset) { g.n[0] = g.n[1] = 0; g.n_fresh = 0; }
+        const bool do_reset = env_tick<MODE, false, FEAT>(g, p, e, env, t, tid, bx);
+        if (do_reset) g.clear();
         else g.commit();
     }
     const uint2 m = pack_meta(e);
-    st.hot[i] = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
+    st.hot[i] = make_uint4(m.x, m.y, (uint32_t)g.n0 | ((uint32_t)g.n1 << 16), 0u);
     if (MODE == MODE_STEP) g.store_dirty(st, i);
 }
 
@@ -200,11 +230,13 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
     const long long gi = p.state_off + (owner ? env : env0);
     EnvState e = unpack_meta(make_uint2(0, 0));
     TrailCells g;
-    g.W = p.W; g.H = p.H; g.n[0] = g.n[1] = 0; g.cold = st.cold + gi * st.cw; g.dirty = 0; g.n_fresh = 0;
+    g.W = p.W; g.H = p.H; g.cold = st.cold + gi * st.cw;
+    g.start(0, 0);
+    g.blank();
     if (owner) {
         const uint4 hdr = st.hot[gi];
         e = unpack_meta(make_uint2(hdr.x, hdr.y));
-        g.n[0] = (int)(hdr.z & 0xFFFFu); g.n[1] = (int)(hdr.z >> 16);
+        g.start((int)(hdr.z & 0xFFFFu), (int)(hdr.z >> 16));
         if (MODE == MODE_STEP) g.load_hot(st, gi, kTrailHot);
         if (MODE == MODE_OBSERVE) emit_extra(p, env);
     }
@@ -213,7 +245,7 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
     for (int t = 0; t < T; ++t) {
         if (MODE == MODE_STEP && owner) {
             BoxRegs bx;
-            if (env_tick<MODE_STEP, false>(g, p, e, env, t, tid, bx)) { g.n[0] = g.n[1] = 0; g.n_fresh = 0; }
+            if (env_tick<MODE_STEP, false>(g, p, e, env, t, tid, bx)) g.clear();
             else g.commit();
         }
         if (!(MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1)) continue;
@@ -224,7 +256,7 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
         for (int src = 0; src < gpw; ++src) {  // warp-uniform loop over this warp's games
             if (warp * gpw + src >= nG) break;
             const long long senv = env0 + warp * gpw + src;
-            const int n1 = __shfl_sync(0xFFFFFFFFu, g.n[0], src), n2 = __shfl_sync(0xFFFFFFFFu, g.n[1], src);
+            const int n1 = __shfl_sync(0xFFFFFFFFu, g.n0, src), n2 = __shfl_sync(0xFFFFFFFFu, g.n1, src);
             const int hr1 = __shfl_sync(0xFFFFFFFFu, e.r1, src), hc1 = __shfl_sync(0xFFFFFFFFu, e.c1, src);
             const int hr2 = __shfl_sync(0xFFFFFFFFu, e.r2, src), hc2 = __shfl_sync(0xFFFFFFFFu, e.c2, src);
             char* gbase = obase + (size_t)senv * 2 * P * C * ES;
@@ -287,7 +319,7 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
     }
     if (MODE == MODE_STEP && owner) {
         const uint2 m = pack_meta(e);
-        st.hot[gi] = make_uint4(m.x, m.y, (uint32_t)g.n[0] | ((uint32_t)g.n[1] << 16), 0u);
+        st.hot[gi] = make_uint4(m.x, m.y, (uint32_t)g.n0 | ((uint32_t)g.n1 << 16), 0u);
     }
 }
 
@@ -328,8 +360,10 @@ int launch_step_trail_obs(const StepParams& p, int mode, int od, int enc_kind, c
 
 int launch_step_trail(const StepParams& p, int mode, cudaStream_t s) {
     const unsigned grid = (unsigned)(((long long)p.N + kTrailThreads - 1) / kTrailThreads);
-    if (mode == MODE_STEP) step_trail_kernel<MODE_STEP><<<grid, kTrailThreads, 0, s>>>(p);
-    else if (mode == MODE_RESET) step_trail_kernel<MODE_RESET><<<grid, kTrailThreads, 0, s>>>(p);
+    const bool lean = p.slide_mode == TRON_SLIDE_NONE && (p.actions != nullptr || p.eps_thr < 0);
+    if (mode == MODE_STEP && lean) step_trail_kernel<MODE_STEP, 0><<<grid, kTrailThreads, 0, s>>>(p);
+    else if (mode == MODE_STEP) step_trail_kernel<MODE_STEP, FEAT_ALL><<<grid, kTrailThreads, 0, s>>>(p);
+    else if (mode == MODE_RESET) step_trail_kernel<MODE_RESET, 0><<<grid, kTrailThreads, 0, s>>>(p);
     else return TRON_ERR_UNSUPPORTED;
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }

@@ -138,7 +138,10 @@ struct LoggedByteCells {
 // One tick of the env whose cells start at `g`.  Updates `e` (fresh game state if it returns true = "rebuild this grid"),
 // writes reward/done/winner/ep_len for (tick t, env) and adds to the striped statistics.  TRACK maintains the dirty boxes.
 // pre_actions: the two actions already fetched (and range-folded by read_action) by a kernel that prefetches its inputs.
-template <int MODE, bool TRACK, class Cells>
+// FEAT: which optional paths are compiled in -- FEAT_SLIDE the ice/temper slide modes, FEAT_EPS the epsilon-greedy proxy policy.  A
+// launcher picks the leanest instantiation the call allows (fewer instructions and registers for the plain tick).
+enum : int { FEAT_SLIDE = 1, FEAT_EPS = 2, FEAT_ALL = 3 };
+template <int MODE, bool TRACK, int FEAT = FEAT_ALL, class Cells>
 __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState& e, long long env, int t, int tid, BoxRegs& bx,
                                          const int* pre_actions = nullptr) {
     bool do_reset = false;
@@ -159,7 +162,7 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
         } else {
             const uint4 r = philox(p.seed, ctr, genv, TAG_ACTION, 0);
             a1 = (int)(r.x >> 30); a2 = (int)(r.y >> 30);
-            if (p.eps_thr >= 0 && !(e.flags & TRON_FLAG_DONE)) {  // epsilon-greedy proxy: a random FREE neighbour unless exploring
+            if ((FEAT & FEAT_EPS) && p.eps_thr >= 0 && !(e.flags & TRON_FLAG_DONE)) {  // epsilon-greedy proxy: a random FREE neighbour unless exploring
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const uint32_t w = i ? r.y : r.x;
@@ -202,7 +205,7 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
             const int dr1 = (a1 == 2) - (a1 == 0), dc1 = (a1 == 1) - (a1 == 3);
             const int dr2 = (a2 == 2) - (a2 == 0), dc2 = (a2 == 1) - (a2 == 3);
             r1 += dr1; c1 += dc1;
-            if (p.slide_mode != TRON_SLIDE_NONE) {  // reference game.py:163-178
+            if ((FEAT & FEAT_SLIDE) && p.slide_mode != TRON_SLIDE_NONE) {  // reference game.py:163-178
                 uint4 sr = make_uint4(0, 0, 0, 0);
                 if (p.slide_mode >= TRON_SLIDE_ICE) sr = philox(p.seed, ctr, genv, TAG_SLIDE, 0);
                 char4 tp = make_char4(0, 0, 0, 0);

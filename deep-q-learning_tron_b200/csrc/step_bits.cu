@@ -207,9 +207,9 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
     uint8_t* tflag = (uint8_t*)(tile + ((p.G * C + 15) & ~15));  // [G] "this game just finished" (terminal-frame pass)
     PlaneTab* smtab = (PlaneTab*)(tflag + ((p.G + 15) & ~15));   // [2][3] tables for the linear schedule
     const int tid = threadIdx.x;
-    // store schedule: linear (one contiguous 512-byte run per warp store) for the two-plane 10x10 kernels; the slide kernels
-    // spend more issue slots in the tick and are faster with the per-plane schedule.  TRON_OPT_ENCODE_VARIANT 2 / 8 force one.
-    const bool linear = W_T == 10 && ((p.variant & 2) || (!SLIDE && !(p.variant & 8)));
+    // store schedule: linear (one contiguous 512-byte run per warp store) on the 10x10 board; TRON_OPT_ENCODE_VARIANT 8 selects the
+    // per-plane schedule of encode_tile() for comparison
+    const bool linear = W_T == 10 && !(p.variant & 8);
     if (LP > 0 && linear) {
         if (tid < 6) smtab[tid] = p.tab[tid / 3][tid % 3];
         __syncthreads();

@@ -60,7 +60,8 @@ def main():
     if key:
         tp = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
         t = json.load(open(tp)) if os.path.exists(tp) else {}
-        t[key] = sum(l["dram_bytes_total"] for l in launches) / len(launches)
+        t[key] = {"bytes": sum(l["dram_bytes_total"] for l in launches) / len(launches), "source": "profiles/" + os.path.basename(out) + ".json",
+                  "kernel": launches[0]["kernel"][:80], "launches_averaged": len(launches)}
         json.dump(t, open(tp, "w"), indent=1)
     for l in launches:
         print(l["kernel"][:60], "%.1f us" % (l["gpu__time_duration.sum"] * 1e6), "%.3f GB dram" % (l["dram_bytes_total"] / 1e9), "%.0f GB/s" % l.get("dram_GBps", 0))

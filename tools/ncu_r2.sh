@@ -5,6 +5,7 @@ prof() { # name skip cmd...
   echo "$name rc=$?"
 }
 prof trail64 3 python tools/profile_case.py 2097152 64 bf16 none 4 trail --actions rng
+prof trail64_lazy 3 python tools/profile_case.py 2097152 64 bf16 none 4 trail --actions rng --variant 4
 prof bits_temper 4 python tools/profile_case.py 4194304 10 bf16 lut1 4 bits --slide temper --actions rng
 prof bits10_lut1 4 python tools/profile_case.py 4194304 10 bf16 lut1 4 bits10
 prof bits10_popup3 4 python tools/profile_case.py 2097152 10 bf16 popup3 4 bits10

@@ -72,18 +72,22 @@ def main():
     quick = "--quick" in sys.argv
     M = 1 << 20
     if "--r2" in sys.argv:  # round-2 focus: training encodings, temper on bit planes, config #5, encode-schedule variants
-        for v in (0, 1, 2, 3):
+        for v in (0, 8):
             run("10x10 bf16 1-plane bits10 variant %d" % v, 4 * M, 10, "bf16", "lut1", layout="bits10", variant=v)
             run("10x10 bf16 pop_up3 bits10 variant %d" % v, 2 * M, 10, "bf16", "popup3", layout="bits10", variant=v)
             run("10x10 bf16 pop_up3+const bits10 variant %d" % v, 2 * M, 10, "bf16", "popup3_const", layout="bits10", variant=v)
         run("10x10 bf16 pop_up3 tile8", 2 * M, 10, "bf16", "popup3")
-        for v in (0, 1, 2, 3):
+        for v in (0, 8):
             run("10x10 temper bf16 1-plane bits variant %d" % v, 4 * M, 10, "bf16", "lut1", layout="bits", slide_mode="temper", actions="rng", variant=v)
         run("10x10 temper bf16 1-plane tile8", 4 * M, 10, "bf16", "lut1", layout="tile8", slide_mode="temper", actions="rng")
         run("10x10 temper bf16 pop_up3 bits", 2 * M, 10, "bf16", "popup3", layout="bits", slide_mode="temper", actions="rng")
+        run("10x10 ice bf16 1-plane bits", 4 * M, 10, "bf16", "lut1", layout="bits", slide_mode="ice", actions="rng")
+        run("10x10 f32 1-plane bits10", 2 * M, 10, "f32", "lut1", layout="bits10")
+        run("10x10 i8 1-plane bits10", 4 * M, 10, "i8", "lut1", layout="bits10")
+        run("10x10 pure step bits10", 8 * M, 10, "bf16", "none", layout="bits10")
         run("8x8 bf16 1-plane bits", 4 * M, 8, "bf16", "lut1", layout="bits", actions="rng")
         run("8x8 bf16 1-plane tile8", 4 * M, 8, "bf16", "lut1", layout="tile8", actions="rng")
-        for v in (0, 4):
+        for v in (0, 4, 16, 20):
             run("64x64 pure step trail, tape, variant %d" % v, 2 * M, 64, "bf16", "none", steps=20, layout="trail", variant=v)
             run("64x64 pure step trail, in-kernel policy, variant %d" % v, 2 * M, 64, "bf16", "none", steps=20, layout="trail", actions="rng", variant=v)
             run("64x64 pure step trail, eps-greedy 0.1 (long episodes), variant %d" % v, 2 * M, 64, "bf16", "none", steps=20, warmup=60, layout="trail", actions="rng",

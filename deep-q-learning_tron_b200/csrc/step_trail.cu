@@ -14,7 +14,10 @@
 // them.  A tick of thread-per-game is then four fully coalesced 512-byte warp loads, one coalesced header store and one
 // coalesced store of the uint4 that received this tick's entries: the kernel streams at HBM bandwidth instead of paying one
 // DRAM row activation per game (round 1 kept a game's record contiguous, 16 KB apart from its neighbours: 0.34 of peak).
-// Only episodes longer than 12 ticks touch the cold area.
+// Only episodes longer than 12 ticks touch the cold area.  Unused entries of the hot words hold the impossible key 0xFFFF (see
+// TrailCells), which makes "is this cell free?" a branch-free packed-minimum over the words (VIMNMX3.U16x2, 1.5 instructions per
+// list word); the kernel is instruction-issue-bound, not bandwidth-bound (profiles/r2_step_trail_64x64_2M.json: issue active 75 %,
+// DRAM 29 %), so instruction count is what the layout and these tricks buy.
 #include "launch.h"
 #include "step_kernels.cuh"
 
@@ -56,8 +59,9 @@ __device__ __forceinline__ uint32_t zero_halves(uint32_t x) {
 }
 
 struct TrailCells {
-    // list words 0..11 in registers.  Entries at positions >= n (stale leftovers of an earlier game) are overwritten with the
-    // impossible key 0xFFFF when the words are loaded, so that get() needs no validity test per entry.
+    // list words 0..11 in registers.  INVARIANT of the hot arrays (memory and registers): an entry at a position >= n holds the
+    // impossible key 0xFFFF, so that get() needs no validity test per entry.  Whoever empties a list (reset, auto-reset, import)
+    // writes the placeholders back; the cold words (positions >= 12) carry no such guarantee and are tested against n.
     uint32_t hot[kTrailHot];
     uint32_t* cold;           // this game's cold words (list words 12..)
     int n0, n1;               // entries per player at the start of the tick (those are in hot[] / cold[])
@@ -72,21 +76,22 @@ struct TrailCells {
 #pragma unroll
         for (int w = 0; w < kTrailHot; ++w) hot[w] = 0xFFFFFFFFu;
     }
-    __device__ __forceinline__ void clear() {  // fresh game: empty lists
+    __device__ __forceinline__ void clear() {  // fresh game: empty lists; the hot uint4s that held entries go back as placeholders
+        const int used = min(kTrailHot, max(n0, n1));
+        dirty |= (used > 0 ? 2u : 0u) | (used > 4 ? 4u : 0u) | (used > 8 ? 8u : 0u);
         n0 = n1 = 0; fb = fs = 0xFFFFFFFFu;
         blank();
-    }
-    __device__ __forceinline__ void sanitize() {
-#pragma unroll
-        for (int w = 0; w < kTrailHot; ++w) hot[w] |= (w >= n0 ? 0x0000FFFFu : 0u) | (w >= n1 ? 0xFFFF0000u : 0u);
     }
 
     __device__ __forceinline__ int get(int r, int c) const {
         if (r < 0 || c < 0 || r >= W || c >= H) return TRON_TILE_WALL;
         const uint32_t key = (uint32_t)(r & 0x7F) | ((uint32_t)c << 8), key2 = key | (key << 16);
-        uint32_t hit = zero_halves((fb & 0xFF7FFF7Fu) ^ key2) | zero_halves((fs & 0xFF7FFF7Fu) ^ key2);
+        // per 16-bit half: (entry without its slide flag) ^ key is zero iff the entry is this cell; a running packed minimum
+        // (VIMNMX3.U16x2, two list words per instruction) ends at zero iff any entry matched
+        uint32_t acc = __vimin3_u16x2(0xFFFFFFFFu, (fb & 0xFF7FFF7Fu) ^ key2, (fs & 0xFF7FFF7Fu) ^ key2);
 #pragma unroll
-        for (int w = 0; w < kTrailHot; ++w) hit |= zero_halves((hot[w] & 0xFF7FFF7Fu) ^ key2);
+        for (int w = 0; w < kTrailHot; w += 2) acc = __vimin3_u16x2(acc, (hot[w] & 0xFF7FFF7Fu) ^ key2, (hot[w + 1] & 0xFF7FFF7Fu) ^ key2);
+        uint32_t hit = zero_halves(acc);
         const int nmax = max(n0, n1);
         for (int w = kTrailHot; w < nmax; ++w) {  // long episode: the rest of the lists, straight from memory
             const uint32_t z = zero_halves((cold[w - kTrailHot] & 0xFF7FFF7Fu) ^ key2);
@@ -139,15 +144,14 @@ struct TrailCells {
         }
         fb = fs = 0xFFFFFFFFu;
     }
+    // upto_words: list words that can hold valid entries or receive this call's appends; the others are placeholders by the invariant
     __device__ __forceinline__ void load_hot(const TrailStore& st, long long i, int upto_words) {
-        // upto_words: list words that can hold valid entries (lazy variant) or kTrailHot
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
             uint4 v = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
             if (4 * q < upto_words) v = st.hot[(long long)(1 + q) * st.SN + i];
             hot[4 * q] = v.x; hot[4 * q + 1] = v.y; hot[4 * q + 2] = v.z; hot[4 * q + 3] = v.w;
         }
-        sanitize();
     }
     __device__ __forceinline__ void store_dirty(const TrailStore& st, long long i) {
 #pragma unroll
@@ -170,23 +174,26 @@ __global__ void __launch_bounds__(kTrailThreads, MIN_CTAS) step_trail_kernel(con
     g.W = p.W; g.H = p.H; g.cold = st.cold + i * st.cw;
     g.start((int)(hdr.z & 0xFFFFu), (int)(hdr.z >> 16));
     if (MODE == MODE_STEP) {
-        // lazy variant: a list word beyond max(n1,n2) holds nothing valid, and this tick appends at most two entries per player,
-        // so only the uint4s up to word max(n)+1 are needed (second round trip only for games older than 2 ticks)
-        const int need = (p.variant & 4) ? min(kTrailHot, max(g.n0, g.n1) + 2 * p.T) : kTrailHot;
-        g.load_hot(st, i, need);
+        // a list word beyond max(n0, n1) holds nothing valid and a tick appends at most two entries per player, so only the
+        // uint4s up to word max(n) + 2T are fetched (one 16-byte load for young games; the others are placeholders by the invariant)
+        g.load_hot(st, i, min(kTrailHot, max(g.n0, g.n1) + 2 * p.T));
     } else {
-        g.blank();  // MODE_RESET never looks at the lists; games that are not reset keep their counts
+        g.blank();  // MODE_RESET never looks at the lists; games that are not reset keep theirs
     }
     const int T = MODE == MODE_STEP ? p.T : 1;
     for (int t = 0; t < T; ++t) {
         BoxRegs bx;
         const bool do_reset = env_tick<MODE, false, FEAT>(g, p, e, env, t, tid, bx);
-        if (do_reset) g.clear();
-        else g.commit();
+        if (do_reset) {
+            g.clear();
+            if (MODE == MODE_RESET) g.dirty = 0xEu;  // an explicit reset establishes the invariant whatever the memory held before
+        } else {
+            g.commit();
+        }
     }
     const uint2 m = pack_meta(e);
     st.hot[i] = make_uint4(m.x, m.y, (uint32_t)g.n0 | ((uint32_t)g.n1 << 16), 0u);
-    if (MODE == MODE_STEP) g.store_dirty(st, i);
+    g.store_dirty(st, i);  // MODE_RESET: the placeholders of the games that were reset
 }
 
 // ---- fused tick + observation planes on the trail-list state ------------------------------------------------------------
@@ -414,6 +421,7 @@ __global__ void trail_import_kernel(const StepParams p, const int8_t* __restrict
     uint4 hdr = st.hot[i];
     if (tiles) {
         const int Hc = H + 2;
+        for (int q = 1; q <= 3; ++q) st.hot[(long long)q * st.SN + i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);  // invariant: unused = 0xFFFF
         const int8_t* t = tiles + (size_t)env * (W + 2) * (H + 2);
         int n1 = 0, n2 = 0;
         for (int r = 0; r < W; ++r)

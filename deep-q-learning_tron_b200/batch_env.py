@@ -71,8 +71,8 @@ class BatchedTron:
 
     obs layout: [N, 2, P, width+2, height+2]; obs[:, p] is player p+1's NCHW view (zero-copy).
     reward: name in abi.REWARD_POLICIES or a 5-tuple (step_base, step_per_tick, win, lose, draw).
-    layout: "tile8" (int8 grid, default), "bits10" (32-byte bit planes, 10x10 without slide modes), "bits" (48-byte bit planes, any
-    board with W*H <= 128, every mode), "trail" (trail lists, made for pure ticks on large grids) or "auto" (the fastest one that fits).
+    layout: "auto" (default: the fastest one that fits), "tile8" (int8 grid), "bits10" (32-byte bit planes, 10x10 without slide
+    modes), "bits" (48-byte bit planes, any board with W*H <= 128, every mode) or "trail" (trail lists, made for pure ticks on large grids).
     game_params: keep the per-game parameters Game.__init__ draws for every game (weight x2, degree; tron/game.py:83,87) in
     `self.slide_params` ([N,4] int8 {degree, weight1, weight2, 0}) and the [degree, weight] side features of the games the latest
     observation shows (Game.get_multy, tron/game.py:137-139) in `self.extra` ([N,2,2] f32: per player {degree, weight_p}).
@@ -81,7 +81,7 @@ class BatchedTron:
 
     def __init__(self, n_envs, width=10, height=10, device="cuda", obs_dtype=torch.bfloat16, obs_enc="lut1", lut=None,
                  const_plane=0.0, reward="ddqn", auto_reset=True, seed=0, env_id_base=0, slide_mode=None,
-                 slide_rate=0.15, collect_stats=True, layout="tile8", spawn_mode="uniform",
+                 slide_rate=0.15, collect_stats=True, layout="auto", spawn_mode="uniform",
                  policy="uniform", policy_epsilon=0.0, game_params=None):
         _lib.require_cuda()
         self.lib = _lib.load()

@@ -157,47 +157,6 @@ __device__ __forceinline__ void expand_tile(const BitCells<SLIDE, W_T>& g, int r
     else expand_tile_generic<SLIDE>(g, r1, c1, r2, c2, dst);
 }
 
-// ------------------------------------------------------------------------------------------------ linear encode schedule
-// The observation of one game is one contiguous run of 2*P planes; here item j of a game is its j-th 16-byte chunk, whatever
-// plane it falls into, so every warp-wide store is ONE contiguous 512-byte run (encode_tile() instead issues one store per
-// (player, plane) whose lanes follow the cells, i.e. 2*P interleaved runs of 288 B).  Costs a selector recomputation per chunk.
-template <int OD, int LP, bool CP>
-__device__ __forceinline__ void encode_tile_linear144(const int8_t* tile, int nG, long long env0, const StepParams& p, int t, const PlaneTab* smtab,
-                                                      void* out = nullptr, const uint8_t* only = nullptr) {
-    constexpr int C = 144, ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1, P = (LP + (CP ? 1 : 0)) > 0 ? LP + (CP ? 1 : 0) : 1;
-    constexpr int CPC = 16 / ES;           // cells per 16-byte chunk: 8 (bf16), 4 (f32), 16 (i8)
-    constexpr int CPP = C / CPC;           // chunks per plane: 18, 36, 9
-    constexpr int CPG = 2 * P * CPP;       // chunks per game
-    const size_t tick_off = (size_t)t * (size_t)p.N * CPG * 16;
-    uint4* obase = (uint4*)((char*)(out ? out : p.obs) + tick_off) + (size_t)env0 * CPG;
-    for (int it = threadIdx.x; it < nG * CPG; it += kBitsThreads) {
-        const int e = it / CPG, j = it - e * CPG;
-        if (only && !only[e]) continue;
-        const int pq = j / CPP, ch = j - pq * CPP, pl = pq / P, q = pq - pl * P;
-        uint32_t o[4];
-        if (CP && q == LP) {
-            uint32_t f[Enc4<OD>::WORDS];
-            Enc4<OD>::fill(p.const_plane, f);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) o[k] = f[k % Enc4<OD>::WORDS];
-        } else {
-            const PlaneTab tb = smtab[pl * 3 + q];
-            const int8_t* cells = tile + e * C + ch * CPC;
-            if constexpr (CPC == 8) {
-                const uint2 w = *(const uint2*)cells;
-                Enc4<OD>::run(tb, cell_selector(w.x), o); Enc4<OD>::run(tb, cell_selector(w.y), o + 2);
-            } else if constexpr (CPC == 4) {
-                Enc4<OD>::run(tb, cell_selector(*(const uint32_t*)cells), o);
-            } else {
-                const uint4 w = *(const uint4*)cells;
-                Enc4<OD>::run(tb, cell_selector(w.x), o); Enc4<OD>::run(tb, cell_selector(w.y), o + 1);
-                Enc4<OD>::run(tb, cell_selector(w.z), o + 2); Enc4<OD>::run(tb, cell_selector(w.w), o + 3);
-            }
-        }
-        st_cs(obase + it, make_uint4(o[0], o[1], o[2], o[3]));
-    }
-}
-
 // ------------------------------------------------------------------------------------------------ the kernel
 template <bool SLIDE, int W_T, int OD, int LP, bool CP, int CH, int MODE>
 __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParams p) {
@@ -241,7 +200,7 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
                 }
                 __syncthreads();
                 const int tt = p.obs_every_tick ? t : 0;
-                if (linear) encode_tile_linear144<OD, LP, CP>(tile, nG, env0, p, tt, smtab, p.obs_term, tflag);
+                if (linear) encode_tile_linear144<kBitsThreads, OD, LP, CP>(tile, nG, env0, p, tt, smtab, p.obs_term, tflag);
                 else encode_tile<(W_T == 10 ? 144 : 0), kBitsThreads, OD, LP, CP, CH>(tile, nG, env0, p, tt, p.obs_term, tflag);
                 __syncthreads();
             }
@@ -253,7 +212,7 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
                 if (owner) expand_tile<SLIDE, W_T, false>(g, e.r1, e.c1, e.r2, e.c2, tile + tid * C);
                 __syncthreads();
                 const int tt = (MODE == MODE_STEP && p.obs_every_tick) ? t : 0;
-                if (linear) encode_tile_linear144<OD, LP, CP>(tile, nG, env0, p, tt, smtab);
+                if (linear) encode_tile_linear144<kBitsThreads, OD, LP, CP>(tile, nG, env0, p, tt, smtab);
                 else encode_tile<(W_T == 10 ? 144 : 0), kBitsThreads, OD, LP, CP, CH>(tile, nG, env0, p, tt);
                 if (T > 1) __syncthreads();  // the tile is rewritten by the next tick
             }

@@ -8,7 +8,7 @@ namespace tron {
 constexpr int kThreads = 128;
 
 inline size_t tile_smem_bytes(int G, int C) {
-    return (size_t)((G * C + 15) & ~15) + (size_t)((C + 15) & ~15) + (size_t)G * 4 + (size_t)G + 8 + 16;
+    return (size_t)((G * C + 15) & ~15) + (size_t)((C + 15) & ~15) + (size_t)G * 4 + (size_t)G + 8 + 16 + 16 + 6 * sizeof(PlaneTab);
 }
 
 template <int C_T, int OD, int LP, bool CP, int CH, int MODE>

@@ -128,6 +128,47 @@ __device__ __forceinline__ void encode_tile(const int8_t* tile, int nG, long lon
             }
         }
 
+// ---- linear encode schedule (10x10 boards) ---------------------------------------------------------
+// The observation of one game is one contiguous run of 2*P planes; here item j of a game is its j-th 16-byte chunk, whatever
+// plane it falls into, so every warp-wide store is ONE contiguous 512-byte run (encode_tile() instead issues one store per
+// (player, plane) whose lanes follow the cells, i.e. 2*P interleaved runs of 288 B).  Costs a selector recomputation per chunk.
+template <int NT, int OD, int LP, bool CP>
+__device__ __forceinline__ void encode_tile_linear144(const int8_t* tile, int nG, long long env0, const StepParams& p, int t, const PlaneTab* smtab,
+                                                      void* out = nullptr, const uint8_t* only = nullptr) {
+    constexpr int C = 144, ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1, P = (LP + (CP ? 1 : 0)) > 0 ? LP + (CP ? 1 : 0) : 1;
+    constexpr int CPC = 16 / ES;           // cells per 16-byte chunk: 8 (bf16), 4 (f32), 16 (i8)
+    constexpr int CPP = C / CPC;           // chunks per plane: 18, 36, 9
+    constexpr int CPG = 2 * P * CPP;       // chunks per game
+    const size_t tick_off = (size_t)t * (size_t)p.N * CPG * 16;
+    uint4* obase = (uint4*)((char*)(out ? out : p.obs) + tick_off) + (size_t)env0 * CPG;
+    for (int it = threadIdx.x; it < nG * CPG; it += NT) {
+        const int e = it / CPG, j = it - e * CPG;
+        if (only && !only[e]) continue;
+        const int pq = j / CPP, ch = j - pq * CPP, pl = pq / P, q = pq - pl * P;
+        uint32_t o[4];
+        if (CP && q == LP) {
+            uint32_t f[Enc4<OD>::WORDS];
+            Enc4<OD>::fill(p.const_plane, f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = f[k % Enc4<OD>::WORDS];
+        } else {
+            const PlaneTab tb = smtab[pl * 3 + q];
+            const int8_t* cells = tile + e * C + ch * CPC;
+            if constexpr (CPC == 8) {
+                const uint2 w = *(const uint2*)cells;
+                Enc4<OD>::run(tb, cell_selector(w.x), o); Enc4<OD>::run(tb, cell_selector(w.y), o + 2);
+            } else if constexpr (CPC == 4) {
+                Enc4<OD>::run(tb, cell_selector(*(const uint32_t*)cells), o);
+            } else {
+                const uint4 w = *(const uint4*)cells;
+                Enc4<OD>::run(tb, cell_selector(w.x), o); Enc4<OD>::run(tb, cell_selector(w.y), o + 1);
+                Enc4<OD>::run(tb, cell_selector(w.z), o + 2); Enc4<OD>::run(tb, cell_selector(w.w), o + 3);
+            }
+        }
+        st_cs(obase + it, make_uint4(o[0], o[1], o[2], o[3]));
+    }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------
 // C_T: cells per env at compile time (0 = runtime), NT threads, OD obs dtype, LP lut planes (0 = no obs),
 // CP const plane, CH cells per encode item (8, 4 or 1; C % CH == 0), MODE.
@@ -147,6 +188,9 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
     ushort2* hidx = (ushort2*)(tmpl + ((C + 15) & ~15));
     uint8_t* rflag = (uint8_t*)(hidx + G);
     uint64_t* bar = (uint64_t*)(((uintptr_t)(rflag + G) + 7) & ~(uintptr_t)7);
+    PlaneTab* smtab = (PlaneTab*)(((uintptr_t)(bar + 1) + 15) & ~(uintptr_t)15);  // [2][3] tables of the linear schedule (10x10 only)
+    constexpr bool kLinear = C_T == 144 && LP > 0;
+    if (kLinear && tid < 6) smtab[tid] = p.tab[tid / 3][tid % 3];  // visible after the first __syncthreads below
 
     const int8_t* gsrc = p.grid + env0 * C;
     const uint32_t tile_bytes = (uint32_t)(nG * C);
@@ -212,7 +256,8 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
             }
             __syncthreads();
             if (LP > 0 && MODE == MODE_STEP && p.obs_term) {  // last frame of the games that just finished, before they are rebuilt
-                encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, p.obs_every_tick ? t : 0, p.obs_term, rflag);
+                if constexpr (kLinear) encode_tile_linear144<NT, OD, LP, CP>(tile, nG, env0, p, p.obs_every_tick ? t : 0, smtab, p.obs_term, rflag);
+                else encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, p.obs_every_tick ? t : 0, p.obs_term, rflag);
                 __syncthreads();
             }
             // ------------------------------------------------------------ phase 2: rebuild reset games
@@ -278,8 +323,15 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
         }
         // ---------------------------------------------------------------- phase 3: observation planes
         if (MODE == MODE_OBSERVE && owner) emit_extra(p, env);
-        if (LP > 0 && (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1))
-            encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, (MODE == MODE_STEP && p.obs_every_tick) ? t : 0);
+        if (LP > 0 && (MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1)) {
+            const int tt = (MODE == MODE_STEP && p.obs_every_tick) ? t : 0;
+            if constexpr (kLinear) {  // one contiguous 512-byte run per warp store (see step_bits.cu); TRON_OPT_ENCODE_VARIANT 8 = per-plane schedule
+                if (!(p.variant & 8)) encode_tile_linear144<NT, OD, LP, CP>(tile, nG, env0, p, tt, smtab);
+                else encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, tt);
+            } else {
+                encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, tt);
+            }
+        }
         if (T > 1) __syncthreads();  // next tick's phase 1 rewrites the tile
     }
     if (MODE != MODE_OBSERVE && bulk_ok && !sparse_wb && tid == 0) bulk_wait_read_all();  // tile must outlive the bulk store's read

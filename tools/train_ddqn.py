@@ -30,27 +30,29 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.algo == "dqn":  # BASELINE config #3 as worded: DQN.py survivor loop, GPU replay, batched self-play
         import DQN
-        out = []
-        model, losses = DQN.train(n_envs=a.envs, iterations=max(1, a.ticks // DQN.GAME_CYCLE), log=lambda it, loss, st: out.append((loss, st)))
-        loss, st = out[-1]
-        print(json.dumps({"config": "DQN survivor loop (DQN.py:135-309 restated), %d envs, 1-plane f32 obs, GPU replay ring" % a.envs,
-                          "ms_per_tick": {"q_forward(2N obs)": st["q_forward_ms_per_tick"], "select+env_step+replay_push": st["env_replay_ms_per_tick"]},
-                          "env_fraction_of_tick": st["env_replay_ms_per_tick"] / (st["env_replay_ms_per_tick"] + st["q_forward_ms_per_tick"]),
-                          "loss": loss, "episodes": st["episodes"], "mean_episode_ticks": st["ep_ticks"] / max(1, st["episodes"])}))
+        tm, cyc = {}, []
+        model, losses = DQN.train(n_envs=a.envs, iterations=max(1, a.ticks // DQN.GAME_CYCLE), timings=tm, on_cycle=lambda c, st: cyc.append(st))
+        print(json.dumps({"config": "DQN survivor loop (DQN.py:135-309 restated), %d envs, 1-plane f32 obs, frame-sharing GPU replay" % a.envs,
+                          "ms_per_tick": {"q_forward(2N obs)": tm["q_forward_ms"] / tm["ticks"], "select+env_step (writes the replay ring)": tm["env_replay_ms"] / tm["ticks"]},
+                          "learn_ms_per_step": tm["learn_ms"] / max(1, tm["learn_steps"]),
+                          "env_fraction_of_tick": tm["env_replay_ms"] / (tm["env_replay_ms"] + tm["q_forward_ms"]),
+                          "loss": losses[-1], "last_cycle": cyc[-1]}))
         sys.exit(0)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
-    logs = []
-    agent, env = DDQN.train(n_envs=a.envs, env_steps=a.ticks, learn_every=a.learn_every, log=lambda t, d: logs.append(d), amp=a.amp)
-    warm = logs[len(logs) // 4:]
-    fw = sum(d["forward_ms"] for d in warm) / len(warm); er = sum(d["env_replay_ms"] for d in warm) / len(warm)
-    lr = sum(d["learn_ms"] for d in warm) / len(warm)
+    tm, cyc = {}, []
+    agent, env = DDQN.train(n_envs=a.envs, env_steps=a.ticks, learn_every=a.learn_every, amp=a.amp, timings=tm, warmup_steps=a.ticks // 4,
+                            on_cycle=lambda c, st: cyc.append(st))
     st = env.stats_dict()
     if rank == 0:
-        print(json.dumps({"config": "DDQN self-play, %d envs/GPU x %d GPU(s), pop_up bf16 obs, GPU replay ring%s" % (a.envs, world, ", bf16 autocast forward" if a.amp else ""),
-                          "ms_per_tick": {"q_forward(2N obs)": fw, "select+env_step+replay_push": er, "sample+learn(+allreduce)": lr},
-                          "env_fraction_of_tick": er / (fw + er + lr), "env_steps_per_s_per_gpu": a.envs / ((fw + er + lr) * 1e-3),
-                          "loss": logs[-1]["loss"], "episodes": st["episodes"], "mean_episode_ticks": st["ep_ticks"] / max(1, st["episodes"]),
-                          "replay_len": len(agent.memory)}))
+        n = tm["ticks"]
+        print(json.dumps({"config": "DDQN self-play, %d envs/GPU x %d GPU(s), pop_up bf16 obs, frame-sharing GPU replay%s" % (a.envs, world, ", bf16 autocast forward" if a.amp else ""),
+                          "ms_per_tick": {"q_forward(2N obs)": tm["q_forward_ms"] / n, "select+env_step (writes the replay ring)": tm["env_replay_ms"] / n,
+                                          "sample+learn": tm["learn_ms"] / n},
+                          "learn_ms_per_step": tm["learn_ms"] / max(1, tm["learn_steps"]),
+                          "allreduce_us_per_call": 1e3 * tm["allreduce_ms"] / max(1, tm["allreduce_calls"]),
+                          "env_fraction_of_tick": tm["env_replay_ms"] / (tm["q_forward_ms"] + tm["env_replay_ms"] + tm["learn_ms"]),
+                          "env_steps_per_s_per_gpu": a.envs * n / ((tm["q_forward_ms"] + tm["env_replay_ms"] + tm["learn_ms"]) * 1e-3),
+                          "episodes": st["episodes"], "mean_episode_ticks": st["ep_ticks"] / max(1, st["episodes"]), "last_cycle": cyc[-1] if cyc else None}))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -14,8 +14,9 @@ def env_for(width, height, slide_mode=None):
     """A cached 1-env BatchedTron with int8 observations and no auto-reset (Game semantics)."""
     key = (width, height, slide_mode)
     if key not in _ctx:
+        # int8 layout: a Map may hold ANY arrangement of tiles (Map.__setitem__), which only the Tile.value grid can represent
         _ctx[key] = BatchedTron(1, width, height, obs_dtype=torch.int8, obs_enc="lut1", auto_reset=False, slide_mode=slide_mode,
-                                collect_stats=False)
+                                collect_stats=False, layout="tile8")
     return _ctx[key]
 
 
@@ -29,7 +30,8 @@ class OneGame:
     def __init__(self, width, height, slide_mode):
         import ctypes as C
         self.key = (width, height, slide_mode)
-        self.env = BatchedTron(1, width, height, obs_dtype=torch.int8, obs_enc="lut1", auto_reset=False, slide_mode=slide_mode, collect_stats=False)
+        self.env = BatchedTron(1, width, height, obs_dtype=torch.int8, obs_enc="lut1", auto_reset=False, slide_mode=slide_mode, collect_stats=False,
+                               layout="tile8")
         c = self.env.C
         self.c = c
         o_obs, o_tiles = 0, (2 * c + 15) & ~15

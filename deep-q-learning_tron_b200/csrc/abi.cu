@@ -332,7 +332,7 @@ int tron_import_grid(void* state, int n_envs, int width, int height, int layout,
     geometry_params(state, n_envs, width, height, layout, p);
     if (layout == TRON_LAYOUT_TRAIL) return launch_trail_import(p, tiles, heads, alive, done, winner, ep_len, s);
     if (tiles && (layout == TRON_LAYOUT_BITS10 || layout == TRON_LAYOUT_BITS)) {
-        if (launch_bits_import(p, tiles, s) != TRON_OK) return TRON_ERR_CUDA;
+        if (launch_bits_import(p, tiles, heads == nullptr, s) != TRON_OK) return TRON_ERR_CUDA;
     } else if (tiles && cudaMemcpyAsync(state, tiles, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
         return TRON_ERR_CUDA;
     }

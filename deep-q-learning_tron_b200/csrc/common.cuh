@@ -91,6 +91,25 @@ __device__ __forceinline__ char4 rng_temper(unsigned long long seed, unsigned lo
                       (signed char)(40 + (int)__umulhi(r.y, 62u)), 0);
 }
 
+// Head positions of a Tile.value grid (for imports that give tiles but no head array): the cell holding P1_HEAD / P2_HEAD, border
+// included; a grid with P2's head only is the head-on state where both heads share the cell (P2's tile is written last,
+// reference game.py:205-214).  packed = r1 | c1 << 8 | r2 << 16 | c2 << 24 as in tron_meta; returns false if no head is found.
+__device__ __forceinline__ bool heads_from_tiles(const int8_t* t, int W, int H, uint32_t& packed) {
+    int r1 = 0, c1 = 0, r2 = 0, c2 = 0;
+    bool f1 = false, f2 = false;
+    for (int i = 0; i < W + 2; ++i)
+        for (int j = 0; j < H + 2; ++j) {
+            const int v = t[i * (H + 2) + j];
+            if (v == TRON_TILE_P1_HEAD) { r1 = i - 1; c1 = j - 1; f1 = true; }
+            else if (v == TRON_TILE_P2_HEAD) { r2 = i - 1; c2 = j - 1; f2 = true; }
+        }
+    if (!f1 && !f2) return false;
+    if (!f1) { r1 = r2; c1 = c2; }
+    if (!f2) { r2 = r1; c2 = c1; }
+    packed = (uint32_t)(uint8_t)r1 | ((uint32_t)(uint8_t)c1 << 8) | ((uint32_t)(uint8_t)r2 << 16) | ((uint32_t)(uint8_t)c2 << 24);
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Blackwell/Hopper async-proxy helpers: 1-D bulk copies (TMA engine, no tensor map) + mbarrier.
 // ---------------------------------------------------------------------------------------------

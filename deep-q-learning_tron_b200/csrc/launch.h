@@ -34,7 +34,7 @@ int launch_trail_import(const StepParams& p, const int8_t* tiles, const int8_t* 
 int launch_step_bits10(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_step_bits(const StepParams& p, int mode, int obs_dtype, int enc_kind, cudaStream_t s);
 int launch_bits_export(const StepParams& p, const void* meta, int8_t* tiles, cudaStream_t s);
-int launch_bits_import(const StepParams& p, const int8_t* tiles, cudaStream_t s);
+int launch_bits_import(const StepParams& p, const int8_t* tiles, bool derive_heads, cudaStream_t s);
 int tile_envs_c144(int n_envs);
 int tile_envs_small_grid(int n_envs);
 int tile_envs_generic(int cells);

@@ -299,7 +299,7 @@ __global__ void bits_export_kernel(const StepParams p, const uint2* __restrict__
 }
 // tiles -> planes: trail tiles set bits (BITS10 stores slide tiles as bodies), everything else is implicit
 template <bool SLIDE, int W_T>
-__global__ void bits_import_kernel(const StepParams p, const int8_t* __restrict__ tiles) {
+__global__ void bits_import_kernel(const StepParams p, const int8_t* __restrict__ tiles, bool derive_heads) {
     const long long env = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.N) return;
     BitCells<SLIDE, W_T> g;
@@ -313,6 +313,8 @@ __global__ void bits_import_kernel(const StepParams p, const int8_t* __restrict_
             else if (v == TRON_TILE_P2_SLIDE) g.put(r, c, SLIDE ? (int)TRON_TILE_P2_SLIDE : (int)TRON_TILE_P2_BODY);
         }
     store_planes(p, env, g);
+    uint32_t packed;
+    if (derive_heads && heads_from_tiles(t, p.W, p.H, packed)) p.meta[env].x = packed;  // the bit planes cannot hold heads: they go into the meta
 }
 int launch_bits_export(const StepParams& p, const void* meta, int8_t* tiles, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + 127) / 128);
@@ -321,11 +323,11 @@ int launch_bits_export(const StepParams& p, const void* meta, int8_t* tiles, cud
     else bits_export_kernel<true, 0><<<grid, 128, 0, s>>>(p, (const uint2*)meta, tiles);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
-int launch_bits_import(const StepParams& p, const int8_t* tiles, cudaStream_t s) {
+int launch_bits_import(const StepParams& p, const int8_t* tiles, bool derive_heads, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + 127) / 128);
-    if (p.layout == TRON_LAYOUT_BITS10) bits_import_kernel<false, 10><<<grid, 128, 0, s>>>(p, tiles);
-    else if (p.W == 10 && p.H == 10) bits_import_kernel<true, 10><<<grid, 128, 0, s>>>(p, tiles);
-    else bits_import_kernel<true, 0><<<grid, 128, 0, s>>>(p, tiles);
+    if (p.layout == TRON_LAYOUT_BITS10) bits_import_kernel<false, 10><<<grid, 128, 0, s>>>(p, tiles, derive_heads);
+    else if (p.W == 10 && p.H == 10) bits_import_kernel<true, 10><<<grid, 128, 0, s>>>(p, tiles, derive_heads);
+    else bits_import_kernel<true, 0><<<grid, 128, 0, s>>>(p, tiles, derive_heads);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 

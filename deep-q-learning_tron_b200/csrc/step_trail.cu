@@ -431,6 +431,8 @@ __global__ void trail_import_kernel(const StepParams p, const int8_t* __restrict
                 else if (v == TRON_TILE_P2_BODY || v == TRON_TILE_P2_SLIDE) ((unsigned short*)st.word(i, n2++))[1] = TrailCells::pack(r, c, v == TRON_TILE_P2_SLIDE);
             }
         hdr.z = (uint32_t)n1 | ((uint32_t)n2 << 16);
+        uint32_t packed;
+        if (!heads && heads_from_tiles(t, W, H, packed)) hdr.x = packed;  // the lists cannot hold heads: they go into the header
     }
     uint32_t f = hdr.y & 0xFFu, k = hdr.y >> 16;
     if (heads) {  // clamp to the representable range [-1, W] x [-1, H]

@@ -258,7 +258,10 @@ int tron_step_many(const tron_step_args* args, tron_stream_t stream);
 int tron_export_grid(const void* state, int n_envs, int width, int height, int layout, int8_t* tiles,
                      int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner, int32_t* ep_len,
                      tron_stream_t stream);
-/* Overwrite state from Tile.value grids + heads + alive (inverse of tron_export_grid; Map.__setitem__ shim). */
+/* Overwrite state from Tile.value grids + heads + alive (inverse of tron_export_grid; Map.__setitem__ shim).  Every array may be
+ * NULL (= keep).  The bit-plane and trail layouts keep heads outside the cell data: with tiles given and heads == NULL they take the
+ * head positions from the P1_HEAD / P2_HEAD tiles of the grid (a grid showing only P2's head is the shared-cell head-on state);
+ * a grid with several head tiles of one player, or slide tiles on TRON_LAYOUT_BITS10, is representable on TRON_LAYOUT_TILE8 only. */
 int tron_import_grid(void* state, int n_envs, int width, int height, int layout, const int8_t* tiles,
                      const int8_t* heads, const uint8_t* alive, const uint8_t* done,
                      const uint8_t* winner, const int32_t* ep_len, tron_stream_t stream);

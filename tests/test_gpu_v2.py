@@ -264,3 +264,25 @@ def test_four_million_envs_bits10_properties():
     assert st["env_steps"] == 12 * N and st["episodes"] == st["p1_wins"] + st["p2_wins"] + st["draws"]
     ex = env.export()
     assert np.array_equal(ex["tiles"][:K].cpu().numpy(), lo.export()["tiles"]) and np.array_equal(ex["tiles"][N - K:].cpu().numpy(), hi.export()["tiles"])
+
+
+# ------------------------------------------------------------------ importing a grid given as tiles only
+@pytest.mark.parametrize("layout,W", [("tile8", 10), ("bits10", 10), ("bits", 10), ("bits", 7), ("trail", 10), ("trail", 20)])
+def test_import_of_tiles_only_recovers_the_heads(layout, W):
+    """the compact layouts keep heads outside the cell data; a grid imported without a head array takes them from its head tiles
+    (incl. heads that crashed into the border and the shared-cell head-on state)"""
+    N = 3000
+    o = oc.OracleEnv(N, W, W, obs_dtype=abi.I8, seed=21, auto_reset=False)
+    o.reset()
+    for t in range(5):
+        o.step()
+    ex = o.export()
+    assert ex["done"].any() and not ex["done"].all()
+    g = GpuEnvNumpy(N, W, W, obs_dtype=abi.I8, seed=99, auto_reset=False, layout=layout)
+    g.reset()
+    g.import_(tiles=ex["tiles"])
+    assert np.array_equal(g.observe(), o.observe())
+    back = g.export()
+    assert np.array_equal(back["tiles"], ex["tiles"])
+    one_head = (ex["tiles"] == 2).sum((1, 2)) == 1  # both heads visible (not the shared-cell case)
+    assert np.array_equal(back["heads"][one_head], ex["heads"][one_head])

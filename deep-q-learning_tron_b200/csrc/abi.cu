@@ -336,7 +336,7 @@ int tron_import_grid(void* state, int n_envs, int width, int height, int layout,
     } else if (tiles && cudaMemcpyAsync(state, tiles, (size_t)n_envs * tron_cells_per_env(width, height), cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
         return TRON_ERR_CUDA;
     }
-    return launch_import_meta((char*)state + mo, n_envs, width, height, heads, alive, done, winner, ep_len, s);
+    return launch_import_meta((char*)state + mo, n_envs, width, height, heads, alive, done, winner, ep_len, layout == TRON_LAYOUT_TILE8 ? tiles : nullptr, s);
 }
 
 int tron_random_actions(uint8_t* actions, int n_envs, uint64_t seed, uint64_t counter, const uint64_t* counter_dev, uint64_t env_id_base,

@@ -41,7 +41,7 @@ int tile_envs_generic(int cells);
 
 int launch_export_meta(const void* meta, int n, int8_t* heads, uint8_t* alive, uint8_t* done, uint8_t* winner, int32_t* ep_len, cudaStream_t s);
 int launch_import_meta(void* meta, int n, int W, int H, const int8_t* heads, const uint8_t* alive, const uint8_t* done, const uint8_t* winner,
-                       const int32_t* ep_len, cudaStream_t s);
+                       const int32_t* ep_len, const int8_t* tiles_for_heads, cudaStream_t s);
 int launch_advance_counter(uint64_t* c, uint64_t delta, cudaStream_t s);
 int launch_random_actions(uint8_t* actions, int n, uint64_t seed, uint64_t counter, const uint64_t* cdev, uint64_t base, cudaStream_t s);
 int launch_select_actions(const void* q, int q_dtype, int n, float eps, uint8_t* actions, uint64_t seed, uint64_t counter, const uint64_t* cdev,

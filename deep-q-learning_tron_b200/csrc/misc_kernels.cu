@@ -23,7 +23,7 @@ __global__ void export_meta_kernel(const uint2* __restrict__ meta, int n, int8_t
 }
 
 __global__ void import_meta_kernel(uint2* __restrict__ meta, int n, int W, int H, const int8_t* heads, const uint8_t* alive,
-                                   const uint8_t* done, const uint8_t* winner, const int32_t* ep_len) {
+                                   const uint8_t* done, const uint8_t* winner, const int32_t* ep_len, const int8_t* tiles_for_heads) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     uint2 m = meta[e];
@@ -33,6 +33,10 @@ __global__ void import_meta_kernel(uint2* __restrict__ meta, int n, int W, int H
         const int8_t* h = heads + 4 * (size_t)e;
         const int r1 = min(max((int)h[0], -1), W), c1 = min(max((int)h[1], -1), H), r2 = min(max((int)h[2], -1), W), c2 = min(max((int)h[3], -1), H);
         m.x = (uint32_t)(uint8_t)r1 | ((uint32_t)(uint8_t)c1 << 8) | ((uint32_t)(uint8_t)r2 << 16) | ((uint32_t)(uint8_t)c2 << 24);
+    }
+    else if (tiles_for_heads) {  // a grid given without a head array: the heads are where its head tiles are
+        uint32_t packed;
+        if (heads_from_tiles(tiles_for_heads + (size_t)e * (W + 2) * (H + 2), W, H, packed)) m.x = packed;
     }
     if (alive) f = (f & ~3u) | (alive[2 * e] ? 1u : 0u) | (alive[2 * e + 1] ? 2u : 0u);
     if (done) f = (f & ~TRON_FLAG_DONE) | (done[e] ? TRON_FLAG_DONE : 0u);
@@ -49,8 +53,8 @@ int launch_export_meta(const void* meta, int n, int8_t* heads, uint8_t* alive, u
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 int launch_import_meta(void* meta, int n, int W, int H, const int8_t* heads, const uint8_t* alive, const uint8_t* done,
-                       const uint8_t* winner, const int32_t* ep_len, cudaStream_t s) {
-    import_meta_kernel<<<(n + 255) / 256, 256, 0, s>>>((uint2*)meta, n, W, H, heads, alive, done, winner, ep_len);
+                       const uint8_t* winner, const int32_t* ep_len, const int8_t* tiles_for_heads, cudaStream_t s) {
+    import_meta_kernel<<<(n + 255) / 256, 256, 0, s>>>((uint2*)meta, n, W, H, heads, alive, done, winner, ep_len, tiles_for_heads);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 

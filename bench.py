@@ -563,7 +563,11 @@ def run_ours(a):
                            "value": world * 131072 * tm4["ticks"] / (tot4 * 1e-3), "unit": UNIT, "n_gpus": world, "ticks": tm4["ticks"], "learn_steps": tm4["learn_steps"],
                            "ms": {"q_forward": max_over_ranks(tm4["q_forward_ms"]), "env_replay": max_over_ranks(tm4["env_replay_ms"]),
                                   "learn": max_over_ranks(tm4["learn_ms"]), "allreduce": max_over_ranks(tm4["allreduce_ms"])},
-                           "allreduce_us_per_call": 1e3 * max_over_ranks(tm4["allreduce_ms"]) / max(1, tm4["allreduce_calls"]), "allreduce_calls": tm4["allreduce_calls"],
+                           "allreduce_us_per_call": {"min": max_over_ranks(tm4["allreduce_us_min"]), "median": max_over_ranks(tm4["allreduce_us_median"]),
+                                                     "max": max_over_ranks(tm4["allreduce_us_max"]),
+                                                     "note": "device time from 'backward finished' to 'reduced gradient ready' on the side stream; includes waiting "
+                                                             "for the slowest rank; overlapped with the next tick's forward + env step"},
+                           "allreduce_calls": tm4["allreduce_calls"],
                            "learn_ms_per_step": max_over_ranks(tm4["learn_ms"]) / max(1, tm4["learn_steps"]),
                            "env_replay_fraction_of_loop": tm4["env_replay_ms"] / (tm4["q_forward_ms"] + tm4["env_replay_ms"] + tm4["learn_ms"]),
                            "acting_forward": "bf16 autocast", "state_layout": tm4["layout"], "replay": tm4["replay"]}

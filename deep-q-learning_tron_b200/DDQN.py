@@ -314,8 +314,12 @@ def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloa
     torch.cuda.synchronize()
     agent.totalloss = float(agent._loss_sum)
     if timings is not None:
+        # device time of each overlapped all-reduce, from "backward finished" to "reduced gradient ready": includes waiting for the
+        # slowest rank to reach the collective, which is why min (~ the collective itself) and median are reported next to the sum
+        ar = [a.elapsed_time(b) for a, b in agent.allreduce_events]
         timings.update(ticks=len(events), q_forward_ms=sum(e[0].elapsed_time(e[1]) for e in events),
                        env_replay_ms=sum(e[1].elapsed_time(e[2]) for e in events), learn_ms=sum(e[2].elapsed_time(e[3]) for e in events),
-                       allreduce_ms=sum(a.elapsed_time(b) for a, b in agent.allreduce_events), allreduce_calls=len(agent.allreduce_events),
+                       allreduce_ms=sum(ar), allreduce_calls=len(ar), allreduce_us_min=1e3 * min(ar) if ar else 0.0,
+                       allreduce_us_median=1e3 * sorted(ar)[len(ar) // 2] if ar else 0.0, allreduce_us_max=1e3 * max(ar) if ar else 0.0,
                        learn_steps=n_learn, replay=replay, layout=env.layout)
     return agent, env

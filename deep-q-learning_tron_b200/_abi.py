@@ -23,6 +23,8 @@ LAYOUT_BITS = 3
 OPT_SPARSE_MIN_CELLS = 1
 OPT_TILE_BYTES = 2
 OPT_ENCODE_VARIANT = 3
+OPT_BITS_CTAS_PER_SM = 4
+OPT_TILE_CTAS_PER_SM = 5
 SLIDE_NONE, SLIDE_TAPE, SLIDE_ICE, SLIDE_TEMPER = 0, 1, 2, 3
 SPAWN_UNIFORM, SPAWN_FAIR = 0, 1
 POLICY_UNIFORM, POLICY_FREE_EPS = 0, 1

@@ -41,7 +41,7 @@ _SIGS = {
     "tron_random_actions": (C.c_int, [_vp, _i, _u64, _u64, _vp, _u64, _vp]),
     "tron_select_actions": (C.c_int, [_vp, _i, _i, _f, _vp, _u64, _u64, _vp, _u64, _vp]),
     "tron_advance_counter": (C.c_int, [_vp, _u64, _vp]),
-    "tron_minimax_actions": (C.c_int, [_vp, _i, _i, _i, _i, _i, _u64, _u64, _vp, _u64, _vp, _vp, _vp]),
+    "tron_minimax_actions": (C.c_int, [_vp, _i, _i, _i, _i, _i, _u64, _u64, _vp, _u64, _vp, _vp, _vp, _vp]),
     "tron_pop_up": (C.c_int, [_vp, _i, _i64, _i, _vp, _i, _vp]),
     "replay_push": (C.c_int, [C.POINTER(abi.ReplayRing), _u64, _vp, _vp, _vp, _vp, _vp, _i, _i64, _vp]),
     "replay_gather": (C.c_int, [C.POINTER(abi.ReplayRing), _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),

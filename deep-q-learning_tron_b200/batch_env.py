@@ -340,20 +340,24 @@ class BatchedTron:
                                                     self.seed, counter, cdev, 2 * self.env_id_base, self._stream()), "tron_select_actions")
         return out.view(-1, 2) if out.numel() == 2 * self.N else out
 
-    def minimax_actions(self, player, tie_mode=1, counter=None, out=None, want_values=False):
+    def minimax_actions(self, player, tie_mode=1, counter=None, out=None, want_values=False, want_ties=False):
         """The move (0..3) the reference's MinimaxPlayer(2, voronoi) would make for `player` (1|2) in every game
-        (tron/minimax.py:296-310).  tie_mode 0 = first best move, 1 = uniform among the best (Philox)."""
+        (tron/minimax.py:296-310).  tie_mode 0 = first best move, 1 = uniform among the best (Philox).
+        want_values: also the [N,4] root values; want_ties: also the [N,4] depth-1 tie counts (see tron_minimax_actions)."""
         tiles = self.state if self.layout == abi.LAYOUT_TILE8 else self.export()["tiles"].contiguous()
         if out is None:
             out = torch.empty(self.N, dtype=torch.uint8, device=self.device)
         vals = torch.empty((self.N, 4), dtype=torch.int32, device=self.device) if want_values else None
+        ties = torch.empty((self.N, 4), dtype=torch.int32, device=self.device) if want_ties else None
         cdev = None
         if counter is None:
             counter, cdev = (0, self.counter_dev.data_ptr()) if self.counter_dev is not None else (self.counter, None)
         with _OnDevice(self.device):
             _lib.check(self.lib.tron_minimax_actions(tiles.data_ptr(), self.N, self.W, self.H, int(player), int(tie_mode), self.seed, counter, cdev,
-                                                     self.env_id_base, out.data_ptr(), _ptr(vals), self._stream()), "tron_minimax_actions")
-        return (out, vals) if want_values else out
+                                                     self.env_id_base, out.data_ptr(), _ptr(vals), _ptr(ties), self._stream()), "tron_minimax_actions")
+        if want_values or want_ties:
+            return (out,) + ((vals,) if want_values else ()) + ((ties,) if want_ties else ())
+        return out
 
     def state_dict(self):
         """Snapshot for checkpoint / resume (the reference only saves network weights; env state here is a few tensors)."""

@@ -15,6 +15,8 @@ namespace tron {
 
 long long g_sparse_min_cells = 1024;  // TRON_OPT_SPARSE_MIN_CELLS
 long long g_encode_variant = 0;       // TRON_OPT_ENCODE_VARIANT
+long long g_tile_ctas_per_sm = 0;    // TRON_OPT_TILE_CTAS_PER_SM
+long long g_bits_ctas_per_sm = 0;    // TRON_OPT_BITS_CTAS_PER_SM (0 = the kernels' own default)
 extern long long g_tile_bytes;
 
 // ---- per-device facts ------------------------------------------------------------------------------
@@ -228,6 +230,8 @@ int tron_set_option(int option, int64_t value) {
     if (option == TRON_OPT_SPARSE_MIN_CELLS && value >= 0) { g_sparse_min_cells = value; return TRON_OK; }
     if (option == TRON_OPT_TILE_BYTES && value >= 1024 && value <= 200 * 1024) { tron::g_tile_bytes = value; return TRON_OK; }
     if (option == TRON_OPT_ENCODE_VARIANT && value >= 0 && value < 256) { g_encode_variant = value; return TRON_OK; }
+    if (option == TRON_OPT_BITS_CTAS_PER_SM && value >= 0 && value <= 32) { g_bits_ctas_per_sm = value; return TRON_OK; }
+    if (option == TRON_OPT_TILE_CTAS_PER_SM && value >= 0 && value <= 32) { g_tile_ctas_per_sm = value; return TRON_OK; }
     return TRON_ERR_INVALID;
 }
 
@@ -357,10 +361,10 @@ int tron_select_actions(const void* q, int q_dtype, int n_rows, float epsilon, u
 }
 
 int tron_minimax_actions(const int8_t* tiles, int n_envs, int width, int height, int player, int tie_mode, uint64_t seed, uint64_t counter,
-                         const uint64_t* counter_dev, uint64_t env_id_base, uint8_t* actions, int32_t* values, tron_stream_t stream) {
+                         const uint64_t* counter_dev, uint64_t env_id_base, uint8_t* actions, int32_t* values, int32_t* child_ties, tron_stream_t stream) {
     if (!tiles || !actions || !geometry_ok(n_envs, width, height) || (player != 1 && player != 2) || (tie_mode != 0 && tie_mode != 1)) return TRON_ERR_INVALID;
     if ((width + 2) * (height + 2) > 256) return TRON_ERR_UNSUPPORTED;
-    return launch_minimax(tiles, n_envs, width, height, player, tie_mode, seed, counter, counter_dev, env_id_base, actions, values, (cudaStream_t)stream);
+    return launch_minimax(tiles, n_envs, width, height, player, tie_mode, seed, counter, counter_dev, env_id_base, actions, values, child_ties, (cudaStream_t)stream);
 }
 
 int tron_pop_up(const void* obs, int obs_dtype, int64_t n_maps, int cells, void* planes, int out_dtype, tron_stream_t stream) {

@@ -47,7 +47,7 @@ int launch_random_actions(uint8_t* actions, int n, uint64_t seed, uint64_t count
 int launch_select_actions(const void* q, int q_dtype, int n, float eps, uint8_t* actions, uint64_t seed, uint64_t counter, const uint64_t* cdev,
                           uint64_t base, cudaStream_t s);
 int launch_minimax(const int8_t* tiles, int n, int W, int H, int player, int tie_mode, uint64_t seed, uint64_t counter, const uint64_t* cdev,
-                   uint64_t base, uint8_t* actions, int32_t* values, cudaStream_t s);
+                   uint64_t base, uint8_t* actions, int32_t* values, int32_t* child_ties, cudaStream_t s);
 int launch_pop_up(const void* obs, int in_dtype, int64_t n_maps, int cells, void* planes, int out_dtype, cudaStream_t s);
 int launch_replay_push(const replay_ring* ring, uint64_t cursor, const void* s, const void* s2, const uint8_t* action, const float* reward,
                        const uint8_t* done, int done_stride, int64_t n, cudaStream_t st);

@@ -90,7 +90,7 @@ __device__ void mm_move(MmMap& gm, int action, int deo) {
 
 __global__ void __launch_bounds__(128) minimax_kernel(const int8_t* __restrict__ tiles, int n, int W, int H, int player, int tie_mode,
                                                       unsigned long long seed, unsigned long long counter, const unsigned long long* counter_dev,
-                                                      unsigned long long base, uint8_t* actions, int* values) {
+                                                      unsigned long long base, uint8_t* actions, int* values, int* child_ties) {
     const int lane = threadIdx.x & 31;
     const long long env = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (env >= n) return;
@@ -109,10 +109,11 @@ __global__ void __launch_bounds__(128) minimax_kernel(const int8_t* __restrict__
     const bool root_blocked = mm_blocked(gm, 1, &mask0);
     const int a = (lane >> 2) & 3, b = lane & 3;
     int leaf = INT_MAX;
+    bool enemy_boxed = false;
     if (!root_blocked && lane < 16 && ((mask0 >> a) & 1)) {
         mm_move(gm, a, 1);
         int mask1 = 0;
-        if (mm_blocked(gm, -1, &mask1)) leaf = 0;  // enemy has no free move: the node keeps its initial value 0 (minimax.py:233)
+        if (mm_blocked(gm, -1, &mask1)) { leaf = 0; enemy_boxed = true; }  // enemy has no free move: the node keeps its initial value 0 (minimax.py:233)
         else if ((mask1 >> b) & 1) {
             mm_move(gm, b, -1);
             leaf = mm_voronoi(gm, p1, p2, qx, qy, ql);
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(128) minimax_kernel(const int8_t* __restrict__
     int v = leaf;
     v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, 1));
     v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, 2));  // min over the enemy's moves
+    const unsigned m_min = __ballot_sync(0xFFFFFFFFu, leaf != INT_MAX && leaf == v), m_box = __ballot_sync(0xFFFFFFFFu, enemy_boxed);
     int val[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -143,12 +145,17 @@ __global__ void __launch_bounds__(128) minimax_kernel(const int8_t* __restrict__
         }
         actions[env] = (uint8_t)act;
         if (values) { values[4 * env] = val[0]; values[4 * env + 1] = val[1]; values[4 * env + 2] = val[2]; values[4 * env + 3] = val[3]; }
+        if (child_ties) {  // what the depth-1 node of each root move draws from the reference's global RNG (see the header)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                child_ties[4 * env + k] = val[k] == INT_MIN ? -1 : ((m_box >> (4 * k)) & 1u) ? 0 : __popc((m_min >> (4 * k)) & 0xFu);
+        }
     }
 }
 
 int launch_minimax(const int8_t* tiles, int n, int W, int H, int player, int tie_mode, uint64_t seed, uint64_t counter, const uint64_t* cdev,
-                   uint64_t base, uint8_t* actions, int32_t* values, cudaStream_t s) {
-    minimax_kernel<<<(n + 3) / 4, 128, 0, s>>>(tiles, n, W, H, player, tie_mode, seed, counter, (const unsigned long long*)cdev, base, actions, values);
+                   uint64_t base, uint8_t* actions, int32_t* values, int32_t* child_ties, cudaStream_t s) {
+    minimax_kernel<<<(n + 3) / 4, 128, 0, s>>>(tiles, n, W, H, player, tie_mode, seed, counter, (const unsigned long long*)cdev, base, actions, values, child_ties);
     return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
 }
 

@@ -20,6 +20,7 @@
 
 namespace tron {
 
+extern long long g_bits_ctas_per_sm;  // TRON_OPT_BITS_CTAS_PER_SM (abi.cu)
 constexpr int kBitsThreads = 128;  // up to one game per thread; p.G games per CTA
 
 // ------------------------------------------------------------------------------------------------ cells
@@ -233,7 +234,15 @@ static size_t bits_smem(int G, int C, int LP) {
 template <bool SLIDE, int W_T, int OD, int LP, bool CP, int CH, int MODE>
 static int launch_bits_one(const StepParams& p, cudaStream_t s) {
     const long long n_tiles = ((long long)p.N + p.G - 1) / p.G;
-    const size_t smem = bits_smem(p.G, p.C, LP);
+    size_t smem = bits_smem(p.G, p.C, LP);
+    if (LP > 0 && MODE == MODE_STEP && n_tiles > 8ll * sm_count()) {
+        // Cap the resident CTAs per SM by padding the dynamic shared memory: floor(228 KB / (smem + 1 KB reserved)) == cap.  The fused
+        // kernels are write streams; with fewer of them per SM than the register limit (8) the DRAM pages see longer bursts
+        // (measured: 4 is best for the two-plane kernels, 5 with the slide plane whose tick phase is longer).
+        const long long cap = g_bits_ctas_per_sm > 0 ? g_bits_ctas_per_sm : (SLIDE ? 5 : 4);
+        const size_t want = (size_t)(228 * 1024) / (size_t)(cap + 1) - 1024 + 256;
+        if (want > smem && want <= 200 * 1024) smem = want;
+    }
     auto kern = step_bits_kernel<SLIDE, W_T, OD, LP, CP, CH, MODE>;
     if (smem > 48 * 1024 && ensure_dynamic_smem((const void*)kern, smem) != TRON_OK) return TRON_ERR_CUDA;
     kern<<<(unsigned)n_tiles, kBitsThreads, smem, s>>>(p);

@@ -6,6 +6,8 @@
 namespace tron {
 
 constexpr int kThreads = 128;
+extern long long g_tile_ctas_per_sm;  // TRON_OPT_TILE_CTAS_PER_SM (abi.cu)
+constexpr long long kDefaultTileCtas = 32;  // no cap until measured
 
 inline size_t tile_smem_bytes(int G, int C) {
     return (size_t)((G * C + 15) & ~15) + (size_t)((C + 15) & ~15) + (size_t)G * 4 + (size_t)G + 8 + 16 + 16 + 6 * sizeof(PlaneTab);
@@ -14,7 +16,13 @@ inline size_t tile_smem_bytes(int G, int C) {
 template <int C_T, int OD, int LP, bool CP, int CH, int MODE>
 int launch_one(const StepParams& p, cudaStream_t s) {
     auto kern = step_tile_kernel<C_T, kThreads, OD, LP, CP, CH, MODE>;
-    const size_t smem = tile_smem_bytes(p.G, p.C);
+    size_t smem = tile_smem_bytes(p.G, p.C);
+    const unsigned n_ctas = (unsigned)(((long long)p.N + p.G - 1) / p.G);
+    const long long cap = g_tile_ctas_per_sm > 0 ? g_tile_ctas_per_sm : kDefaultTileCtas;
+    if (LP > 0 && MODE == MODE_STEP && cap < 32 && n_ctas > 8u * (unsigned)sm_count()) {  // see step_bits.cu: fewer write streams per SM
+        const size_t want = (size_t)(228 * 1024) / (size_t)(cap + 1) - 1024 + 256;
+        if (want > smem && want <= 200 * 1024) smem = want;
+    }
     if (smem > 48 * 1024 && ensure_dynamic_smem((const void*)kern, smem) != TRON_OK) return TRON_ERR_CUDA;
     const unsigned grid = (unsigned)(((long long)p.N + p.G - 1) / p.G);
     kern<<<grid, kThreads, smem, s>>>(p);

@@ -227,7 +227,12 @@ int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* gr
 enum {
     TRON_OPT_SPARSE_MIN_CELLS = 1,
     TRON_OPT_TILE_BYTES = 2, /* shared-memory budget of one tile of games in the generic-size fused kernel (default 18432) */
-    TRON_OPT_ENCODE_VARIANT = 3 /* tuning/experiments: observation store schedule of the bit-plane kernels (0 = default) */
+    TRON_OPT_ENCODE_VARIANT = 3, /* tuning/experiments: observation store schedule of the bit-plane kernels (0 = default) */
+    TRON_OPT_BITS_CTAS_PER_SM = 4, /* resident CTAs per SM of the fused bit-plane kernels (capped by padding the dynamic shared memory).
+                                     0 = default: 4 for the two-plane kernels, 5 with the slide plane -- these kernels are write
+                                     streams and FEWER concurrent streams per SM than the register limit of 8 run faster on B200
+                                     (0.95 -> 0.99 of the measured HBM peak, profiles/r2_cta_cap_sweep.jsonl); 32 = no cap */
+    TRON_OPT_TILE_CTAS_PER_SM = 5 /* the same cap for the fused int8 tile kernels (0 = their default, 32 = no cap) */
 };
 int tron_set_option(int option, int64_t value);
 int tron_cells_per_env(int width, int height);
@@ -281,10 +286,14 @@ int tron_advance_counter(uint64_t* counter_dev, uint64_t delta, tron_stream_t st
 /* Scripted opponent: the action (0..3) MinimaxPlayer(2, voronoi) (tron/minimax.py:58-310) would take for `player` (1|2) in every
  * game.  tiles: device [N, (W+2)(H+2)] Tile.value grids (the TRON_LAYOUT_TILE8 state itself, or tron_export_grid output);
  * grids of at most 256 cells.  tie_mode 0: first best move / UP when boxed in; 1: Philox-uniform (random.choice / randint).
- * values: optional device [N,4] int32 minimax value of each root move (INT32_MIN = move not expanded). */
+ * values: optional device [N,4] int32 minimax value of each root move (INT32_MIN = move not expanded).
+ * child_ties: optional device [N,4] int32, per root move what the reference's depth-1 node draws from the global RNG when it
+ * finishes (minimax.py:233-234,266-267): -1 = move not expanded (no draw), 0 = the enemy is boxed in (one random.randint(1,4)),
+ * L in 1..4 = one random.choice over the L enemy moves that attain the minimum.  Lets a drop-in consume Python's global RNG
+ * exactly like the reference (tron/minimax.py of this package). */
 int tron_minimax_actions(const int8_t* tiles, int n_envs, int width, int height, int player, int tie_mode, uint64_t seed,
                          uint64_t counter, const uint64_t* counter_dev, uint64_t env_id_base, uint8_t* actions,
-                         int32_t* values, tron_stream_t stream);
+                         int32_t* values, int32_t* child_ties, tron_stream_t stream);
 
 /* pop_up on observations that are already encoded (reference tron/util.py:11-37): obs device [n_maps, cells]
  * (TRON_I8|TRON_I32|TRON_I64|TRON_BF16|TRON_F32) -> planes device [n_maps, 3, cells] = {wall, my, enemy}

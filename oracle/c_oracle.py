@@ -261,14 +261,17 @@ def fair_bounds(W, H, px, py):
     return list(b)
 
 
-def minimax_actions(env, player, tie_mode=0, counter=0, want_values=False):
+def minimax_actions(env, player, tie_mode=0, counter=0, want_values=False, want_ties=False):
     """MinimaxPlayer(2, voronoi) decisions for `player` in every game of an OracleEnv (tron/minimax.py)."""
     act = np.zeros(env.N, np.uint8)
     vals = np.zeros((env.N, 4), np.int32)
+    ties = np.zeros((env.N, 4), np.int32)
     rc = lib().oracle_minimax_actions(_p(env.state), env.N, env.W, env.H, player, tie_mode, C.c_uint64(env.seed), C.c_uint64(counter),
-                                      C.c_uint64(env.env_id_base), _p(act), _p(vals))
+                                      C.c_uint64(env.env_id_base), _p(act), _p(vals), _p(ties))
     assert rc == 0, rc
-    return (act, vals) if want_values else act
+    if want_values or want_ties:
+        return (act,) + ((vals,) if want_values else ()) + ((ties,) if want_ties else ())
+    return act
 
 
 def frames_sample_gather(frames, terminal, action, reward, done, frame_dtype, first_tick, n_ticks, k, seed, counter, out_dtype=abi.F32):

@@ -587,29 +587,31 @@ static void mm_next_map(const mm_map* gm, int action /*0..3*/, int deo, mm_map* 
     out->v[ind] = -1;
 }
 /* values of the root's children (INT32_MIN for unexpanded moves); returns 1 if the root is fully blocked */
-static int mm_root_values(const mm_map* gm, int value[4]) {
+/* ties[a]: what the depth-1 node of root move a draws from the global RNG when it finishes: -1 not expanded, 0 one randint (enemy
+ * boxed in, minimax.py:233-234), L = one random.choice over the L minimising enemy moves (minimax.py:266-267) */
+static int mm_root_values(const mm_map* gm, int value[4], int ties[4]) {
     int b0[4];
-    for (int k = 0; k < 4; ++k) value[k] = INT32_MIN;
+    for (int k = 0; k < 4; ++k) { value[k] = INT32_MIN; ties[k] = -1; }
     if (mm_blocked(gm, 1, b0)) return 1;
     for (int a = 0; a < 4; ++a) {
         if (b0[a] == 1) continue;
         mm_map m1; mm_next_map(gm, a, 1, &m1);
         int b1[4];
-        if (mm_blocked(&m1, -1, b1)) { value[a] = 0; continue; }
-        int best = INT32_MAX;
+        if (mm_blocked(&m1, -1, b1)) { value[a] = 0; ties[a] = 0; continue; }
+        int best = INT32_MAX, n_best = 0;
         for (int b = 0; b < 4; ++b) {
             if (b1[b] == 1) continue;
             mm_map m2; mm_next_map(&m1, b, -1, &m2);
             const int v = mm_voronoi(&m2, mm_arg(&m2, 1), mm_arg(&m2, 0));
-            if (v < best) best = v;
+            if (v < best) { best = v; n_best = 1; } else if (v == best) n_best++;
         }
-        value[a] = best;
+        value[a] = best; ties[a] = n_best;
     }
     return 0;
 }
 /* action (0..3) of MinimaxPlayer(2) for `player` (1|2) in every env; values_out [N,4] optional */
 int oracle_minimax_actions(const void* state, int N, int W, int H, int player, int tie_mode, uint64_t seed, uint64_t counter,
-                           uint64_t base, uint8_t* actions, int32_t* values_out) {
+                           uint64_t base, uint8_t* actions, int32_t* values_out, int32_t* ties_out) {
     const int C = cells_of(W, H);
     if (C > MM_MAXC) return TRON_ERR_UNSUPPORTED;
     int8_t lut6[6] = {0, 0, 0, 0, 0, 0}, tab[2 * 3 * 8];
@@ -620,11 +622,11 @@ int oracle_minimax_actions(const void* state, int N, int W, int H, int player, i
         for (int r = 0; r < W + 2; ++r)       /* obs[r][c] -> gm[c][r] */
             for (int c = 0; c < H + 2; ++c)
                 gm.v[c * (W + 2) + r] = tab[(player - 1) * 8 + ((grid[(size_t)e * C + r * (H + 2) + c] + 1) & 7)];
-        int value[4];
+        int value[4], ties[4];
         uint32_t rnd[4];
         philox4x32_10(seed, counter, base + (uint64_t)e, TAG_MINIMAX, (uint32_t)player, rnd);
         int act;
-        if (mm_root_values(&gm, value)) {
+        if (mm_root_values(&gm, value, ties)) {
             act = tie_mode ? (int)(rnd[0] >> 30) : 0;
         } else {
             int best = INT32_MIN, n = 0, list[4];
@@ -634,6 +636,7 @@ int oracle_minimax_actions(const void* state, int N, int W, int H, int player, i
         }
         actions[e] = (uint8_t)act;
         if (values_out) for (int a = 0; a < 4; ++a) values_out[4 * e + a] = value[a];
+        if (ties_out) for (int a = 0; a < 4; ++a) ties_out[4 * e + a] = ties[a];
     }
     return 0;
 }

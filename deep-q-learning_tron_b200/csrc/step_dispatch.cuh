@@ -7,7 +7,8 @@ namespace tron {
 
 constexpr int kThreads = 128;
 extern long long g_tile_ctas_per_sm;  // TRON_OPT_TILE_CTAS_PER_SM (abi.cu)
-constexpr long long kDefaultTileCtas = 32;  // no cap until measured
+// measured defaults (profiles/r2_cta_cap_sweep.jsonl): 5 at 10x10 (+1.5-2 %), 6 for >= 2048 cells (+2 %), no cap in between (8x8, 32x32 lose)
+inline long long default_tile_ctas(int C) { return C == 144 ? 5 : C >= 2048 ? 6 : 32; }
 
 inline size_t tile_smem_bytes(int G, int C) {
     return (size_t)((G * C + 15) & ~15) + (size_t)((C + 15) & ~15) + (size_t)G * 4 + (size_t)G + 8 + 16 + 16 + 6 * sizeof(PlaneTab);
@@ -18,7 +19,7 @@ int launch_one(const StepParams& p, cudaStream_t s) {
     auto kern = step_tile_kernel<C_T, kThreads, OD, LP, CP, CH, MODE>;
     size_t smem = tile_smem_bytes(p.G, p.C);
     const unsigned n_ctas = (unsigned)(((long long)p.N + p.G - 1) / p.G);
-    const long long cap = g_tile_ctas_per_sm > 0 ? g_tile_ctas_per_sm : kDefaultTileCtas;
+    const long long cap = g_tile_ctas_per_sm > 0 ? g_tile_ctas_per_sm : default_tile_ctas(p.C);
     if (LP > 0 && MODE == MODE_STEP && cap < 32 && n_ctas > 8u * (unsigned)sm_count()) {  // see step_bits.cu: fewer write streams per SM
         const size_t want = (size_t)(228 * 1024) / (size_t)(cap + 1) - 1024 + 256;
         if (want > smem && want <= 200 * 1024) smem = want;

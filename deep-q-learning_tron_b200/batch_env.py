@@ -261,6 +261,12 @@ class BatchedTron:
             self._advance(adv)
         return StepResult((obs, reward, done, winner, ep_len))
 
+    def bind_step(self, actions=None, obs=None, reward=None, done=None, winner=None, ep_len=None, obs_terminal=None):
+        """Pre-bound tick for small batches, where Python overhead (not the 3-5 us kernel) sets the pace: validates and packs the
+        argument block ONCE for fixed buffers; each call of the returned object then only bumps the counter and makes the one C
+        call.  Buffers default to freshly allocated ones and are exposed as attributes (.obs .reward .done .winner .ep_len)."""
+        return BoundStep(self, actions, obs, reward, done, winner, ep_len, obs_terminal)
+
     def step_many(self, n_ticks, actions=None, spawn=None, obs_every_tick=True, counter=None):
         """n_ticks ticks in one launch.  actions [T,N,2] or None (RNG), spawn [T,N,4] or None (RNG)."""
         counter, cdev, adv = self._take_counter(counter, int(n_ticks))
@@ -386,6 +392,45 @@ class BatchedTron:
         s = self.stats.view(abi.STATS_SLOTS, abi.STATS_FIELDS).sum(0).tolist()
         return dict(episodes=s[abi.STAT_EPISODES], p1_wins=s[abi.STAT_P1_WINS], p2_wins=s[abi.STAT_P2_WINS], draws=s[abi.STAT_DRAWS],
                     ep_ticks=s[abi.STAT_EP_TICKS], bad_action=s[abi.STAT_BAD_ACTION], env_steps=s[abi.STAT_ENV_STEPS])
+
+
+class BoundStep:
+    """see BatchedTron.bind_step"""
+
+    def __init__(self, env, actions, obs, reward, done, winner, ep_len, obs_terminal):
+        N, dev = env.N, env.device
+        if env.slide_mode == abi.SLIDE_TAPE:
+            raise ValueError("bind_step does not take a slide tape; use step()")
+        if actions is not None and (not torch.is_tensor(actions) or actions.device != dev or tuple(actions.shape) != (N, 2) or
+                                    actions.dtype not in (torch.uint8, torch.int32, torch.int64) or not actions.is_contiguous()):
+            raise ValueError("actions must be a contiguous uint8/int32/int64 tensor of shape (%d, 2) on %s" % (N, dev))
+        shape = (N, 2, env.P, env.W + 2, env.H + 2)
+        self.env, self.actions = env, actions
+        self.obs = (env._out(obs, shape, _TORCH_OF[env.obs_dtype], "obs") if obs is not None else env.new_obs()) if env.P else None
+        self.reward = env._out(reward, (N, 2), torch.float32, "reward") if reward is not None else torch.empty((N, 2), dtype=torch.float32, device=dev)
+        self.done = env._out(done, (N,), torch.uint8, "done") if done is not None else torch.empty(N, dtype=torch.uint8, device=dev)
+        self.winner = env._out(winner, (N,), torch.uint8, "winner") if winner is not None else torch.empty(N, dtype=torch.uint8, device=dev)
+        self.ep_len = env._out(ep_len, (N,), torch.int32, "ep_len")
+        self.obs_terminal = env._out(obs_terminal, shape, _TORCH_OF.get(env.obs_dtype), "obs_terminal") if obs_terminal is not None else None
+        self._args = env._args(actions=_ptr(actions), action_dtype=0 if actions is None else _CODE_OF[actions.dtype], obs=_ptr(self.obs),
+                               reward=self.reward.data_ptr(), done=self.done.data_ptr(), winner=self.winner.data_ptr(), ep_len_out=_ptr(self.ep_len),
+                               obs_terminal=_ptr(self.obs_terminal), counter_dev=None if env.counter_dev is None else env.counter_dev.data_ptr())
+        self._ref = C.byref(self._args)
+        self._fn = env.lib.tron_step
+        self._dev_counter = env.counter_dev is not None
+
+    def __call__(self):
+        env = self.env
+        if not self._dev_counter:
+            self._args.counter = env.counter
+            env.counter += 1
+        with _OnDevice(env.device):
+            rc = self._fn(self._ref, torch.cuda.current_stream(env.device).cuda_stream)
+            if rc:
+                _lib.check(rc, "tron_step")
+            if self._dev_counter:
+                env._advance(1)
+        return self
 
 
 class HostTron:

@@ -286,3 +286,26 @@ def test_import_of_tiles_only_recovers_the_heads(layout, W):
     assert np.array_equal(back["tiles"], ex["tiles"])
     one_head = (ex["tiles"] == 2).sum((1, 2)) == 1  # both heads visible (not the shared-cell case)
     assert np.array_equal(back["heads"][one_head], ex["heads"][one_head])
+
+
+def test_bound_step_equals_step():
+    """bind_step (arguments packed once) is the same tick as step(): external actions, in-kernel policy, device-side counter"""
+    from tron_b200.batch_env import BatchedTron
+    N = 3000
+    for layout in ("bits10", "tile8"):
+        a = BatchedTron(N, 10, 10, obs_dtype=torch.bfloat16, seed=6, layout=layout)
+        b = BatchedTron(N, 10, 10, obs_dtype=torch.bfloat16, seed=6, layout=layout)
+        a.reset(); b.reset()
+        act = torch.zeros((N, 2), dtype=torch.uint8, device="cuda")
+        bound = b.bind_step(actions=act)
+        g = torch.Generator(device="cpu").manual_seed(1)
+        for t in range(12):
+            act.copy_(torch.randint(0, 4, (N, 2), generator=g, dtype=torch.uint8))
+            ra = a.step(act)
+            rb = bound()
+            assert torch.equal(ra.obs.view(torch.int16), rb.obs.view(torch.int16)) and torch.equal(ra.reward, rb.reward) and torch.equal(ra.done, rb.done)
+        pol = b.bind_step()
+        for t in range(6):
+            ra = a.step(); rb = pol()
+            assert torch.equal(ra.obs.view(torch.int16), rb.obs.view(torch.int16)) and torch.equal(ra.winner, rb.winner)
+        assert a.stats_dict() == b.stats_dict()

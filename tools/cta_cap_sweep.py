@@ -10,7 +10,13 @@ import tron_b200  # noqa: E402
 
 M = 1 << 20
 which = sys.argv[1] if len(sys.argv) > 1 else "bits"
-if which == "bits":
+if which == "i8":
+    for cap in (32, 7, 6, 5, 4):
+        tron_b200.lib.check(tron_b200.lib.load().tron_set_option(tron_b200.abi.OPT_BITS_CTAS_PER_SM, cap))
+        run("cap %d: 10x10 i8 1-plane bits10" % cap, 4 * M, 10, "i8", "lut1", layout="bits10", steps=40)
+        run("cap %d: 10x10 i8 pop_up3 bits10" % cap, 4 * M, 10, "i8", "popup3", layout="bits10", steps=40)
+        run("cap %d: 10x10 i8 pop_up3+const bits10" % cap, 4 * M, 10, "i8", "popup3_const", layout="bits10", steps=40)
+elif which == "bits":
     for cap in (32, 7, 6, 5, 4, 3, 2):
         tron_b200.lib.check(tron_b200.lib.load().tron_set_option(tron_b200.abi.OPT_BITS_CTAS_PER_SM, cap))
         run("cap %d: 10x10 bf16 1-plane bits10" % cap, 4 * M, 10, "bf16", "lut1", layout="bits10", steps=40)

@@ -57,6 +57,11 @@ def main():
         w, d = wall_us(fn), device_us(fn)
         out.append(dict(op="tron_step 4096 envs", layout=layout, enc=enc, wall_us_per_call=w, device_us_per_launch=d, env_steps_per_s_wall=4096 / (w * 1e-6),
                         env_steps_per_s_device=4096 / (d * 1e-6)))
+        env2 = BatchedTron(4096, 10, 10, obs_dtype=torch.bfloat16, obs_enc=enc, layout=layout)  # host-side counter: one launch per tick
+        env2.reset()
+        bound = env2.bind_step(obs=obs, reward=rw, done=dn, winner=wn)
+        w = wall_us(bound)
+        out.append(dict(op="bind_step 4096 envs (pre-bound arguments)", layout=layout, enc=enc, wall_us_per_call=w, env_steps_per_s_wall=4096 / (w * 1e-6)))
     for planes, dt in ((3, torch.bfloat16), (1, torch.float32)):
         ring = ReplayRing(1 << 20, (planes, 12, 12), dt)
         ring.cursor = 1 << 20

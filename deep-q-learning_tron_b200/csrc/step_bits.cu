@@ -239,8 +239,8 @@ static int launch_bits_one(const StepParams& p, cudaStream_t s) {
         // Cap the resident CTAs per SM by padding the dynamic shared memory: floor(228 KB / (smem + 1 KB reserved)) == cap.  The fused
         // kernels are write streams; with fewer of them per SM than the register limit (8) the DRAM pages see longer bursts
         // (measured: 4 is best for the two-plane kernels, 5 with the slide plane whose tick phase is longer).
-        // int8 planes move too few bytes per CTA for that (1 plane: 0.93 uncapped, 0.78 at 4): they stay uncapped.
-        const long long cap = g_bits_ctas_per_sm > 0 ? g_bits_ctas_per_sm : (OD == TRON_I8 ? 32 : SLIDE ? 5 : 4);
+        // int8 planes move fewer bytes per CTA: one plane stays uncapped (0.92; 0.78 at 4), three / four planes take 5 (0.985).
+        const long long cap = g_bits_ctas_per_sm > 0 ? g_bits_ctas_per_sm : (OD == TRON_I8 ? (LP == 1 ? 32 : 5) : SLIDE ? 5 : 4);
         const size_t want = (size_t)(228 * 1024) / (size_t)(cap + 1) - 1024 + 256;
         if (want > smem && want <= 200 * 1024) smem = want;
     }

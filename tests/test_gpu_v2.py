@@ -309,3 +309,30 @@ def test_bound_step_equals_step():
             ra = a.step(); rb = pol()
             assert torch.equal(ra.obs.view(torch.int16), rb.obs.view(torch.int16)) and torch.equal(ra.winner, rb.winner)
         assert a.stats_dict() == b.stats_dict()
+
+
+def test_tuning_options_do_not_change_results():
+    """CTA caps (shared-memory padding) and the store-schedule switch are performance knobs only: identical outputs"""
+    from tron_b200 import _lib
+    from tron_b200.batch_env import BatchedTron
+    L = _lib.load()
+    N = 1 << 17  # more than 8 CTAs per SM, so the caps are active
+
+    def run(layout, enc, dtype, slide=None):
+        env = BatchedTron(N, 10, 10, obs_dtype=dtype, obs_enc=enc, seed=12, layout=layout, slide_mode=slide)
+        env.reset()
+        for _ in range(3):
+            r = env.step()
+        return r.obs.clone().view(torch.uint8), r.reward.clone(), env.export()["tiles"].clone()
+    cases = [("bits10", "lut1", torch.bfloat16, None), ("bits10", "popup3", torch.int8, None), ("bits", "lut1", torch.float32, "temper"), ("tile8", "popup3", torch.bfloat16, None)]
+    try:
+        base = [run(*c) for c in cases]
+        for opt, val in ((abi.OPT_BITS_CTAS_PER_SM, 2), (abi.OPT_BITS_CTAS_PER_SM, 32), (abi.OPT_TILE_CTAS_PER_SM, 3), (abi.OPT_ENCODE_VARIANT, 8)):
+            _lib.check(L.tron_set_option(opt, val))
+            for c, want in zip(cases, base):
+                got = run(*c)
+                assert all(torch.equal(g, w) for g, w in zip(got, want)), (opt, val, c)
+            _lib.check(L.tron_set_option(opt, 0))
+    finally:
+        for opt in (abi.OPT_BITS_CTAS_PER_SM, abi.OPT_TILE_CTAS_PER_SM, abi.OPT_ENCODE_VARIANT):
+            L.tron_set_option(opt, 0)

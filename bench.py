@@ -607,6 +607,9 @@ def run_ours(a):
                "python_loop_port": {"value": pv, "unit": UNIT, "cores": cores, "sample": "%d env-steps, pure-Python port of the reference's Game.step loop" % psteps}}
 
     if rank == 0:
+        if e2e is not None and cpu is not None:  # the end-to-end number next to both CPU arms measured in this run
+            e2e["vs_cpu_arms"] = {"c_oracle_port_all_cores": e2e["value"] / cpu["value"], "python_loop_port_all_cores": e2e["value"] / cpu["python_loop_port"]["value"],
+                                  "cores": cpu["cores"], "note": "the driver's e2e_ratio uses the --impl reference line (the live reference's Python loop)"}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i8", "data": "synthetic", "config": workload_config(a, N),
                "timed_region_s": ms * 1e-3, "ms_per_tick": launch_ms, "parity_in_run": parity,

@@ -151,14 +151,13 @@ class Agent:
             self.allreduce_events.append((e0, e1))
             self._pending = e1
         else:
-            self._pending = True
+            self._apply()  # no collective to hide: same order of operations as learn()
         return loss
 
     def learn_finish(self):
         if self._pending is None:
             return
-        if self._pending is not True:
-            torch.cuda.current_stream(self.device).wait_event(self._pending)
+        torch.cuda.current_stream(self.device).wait_event(self._pending)
         self._pending = None
         self._apply()
 

@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
     // store schedule: linear (one contiguous 512-byte run per warp store) on the 10x10 board; TRON_OPT_ENCODE_VARIANT 8 selects the
     // per-plane schedule of encode_tile() for comparison
     const bool linear = W_T == 10 && !(p.variant & 8);
-    if (LP > 0 && linear) {
+    const bool linear4 = W_T == 0 && (C & 3) == 0 && !(p.variant & 8);  // other boards: units of 4 cells (step_kernels.cuh)
+    if (LP > 0 && (linear || linear4)) {
         if (tid < 6) smtab[tid] = p.tab[tid / 3][tid % 3];
         __syncthreads();
     }
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
                 __syncthreads();
                 const int tt = p.obs_every_tick ? t : 0;
                 if (linear) encode_tile_linear144<kBitsThreads, OD, LP, CP>(tile, nG, env0, p, tt, smtab, p.obs_term, tflag);
+                else if (linear4) encode_tile_linear4<kBitsThreads, OD, LP, CP>(tile, C, nG, env0, p, tt, smtab, p.obs_term, tflag);
                 else encode_tile<(W_T == 10 ? 144 : 0), kBitsThreads, OD, LP, CP, CH>(tile, nG, env0, p, tt, p.obs_term, tflag);
                 __syncthreads();
             }
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
                 __syncthreads();
                 const int tt = (MODE == MODE_STEP && p.obs_every_tick) ? t : 0;
                 if (linear) encode_tile_linear144<kBitsThreads, OD, LP, CP>(tile, nG, env0, p, tt, smtab);
+                else if (linear4) encode_tile_linear4<kBitsThreads, OD, LP, CP>(tile, C, nG, env0, p, tt, smtab);
                 else encode_tile<(W_T == 10 ? 144 : 0), kBitsThreads, OD, LP, CP, CH>(tile, nG, env0, p, tt);
                 if (T > 1) __syncthreads();  // the tile is rewritten by the next tick
             }

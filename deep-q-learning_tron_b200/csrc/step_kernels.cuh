@@ -169,6 +169,34 @@ __device__ __forceinline__ void encode_tile_linear144(const int8_t* tile, int nG
     }
 }
 
+// The same linear schedule for any board with C % 4 == 0, in units of 4 cells (4 / 8 / 16 bytes for i8 / bf16 / f32): consecutive
+// lanes write consecutive units of the batch's contiguous observation rows across plane, player and game boundaries, so a warp
+// store is one contiguous run (encode_tile() leaves a partial sector at every 2*C*ES-byte plane end: 8x8 boards ran at 0.73).
+// div_* are exact magic divisions for the small ranges involved (n < 2^20, d < 2^12).
+__device__ __forceinline__ uint32_t magic_of(uint32_t d) { return 0xFFFFFFFFu / d + 1u; }
+__device__ __forceinline__ int magic_div(int n, uint32_t magic, int d) { return d == 1 ? n : (int)__umulhi((uint32_t)n, magic); }
+template <int NT, int OD, int LP, bool CP>
+__device__ __forceinline__ void encode_tile_linear4(const int8_t* tile, int C, int nG, long long env0, const StepParams& p, int t, const PlaneTab* smtab,
+                                                    void* out = nullptr, const uint8_t* only = nullptr) {
+    constexpr int ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1, P = (LP + (CP ? 1 : 0)) > 0 ? LP + (CP ? 1 : 0) : 1;
+    constexpr int UB = 4 * ES;                     // bytes per unit
+    const int UPP = C >> 2, UPG = 2 * P * UPP;     // units per plane / per game
+    const uint32_t m_upg = magic_of((uint32_t)UPG), m_upp = magic_of((uint32_t)UPP);
+    char* obase = (char*)(out ? out : p.obs) + ((size_t)t * (size_t)p.N + (size_t)env0) * (size_t)UPG * UB;
+    for (int it = threadIdx.x; it < nG * UPG; it += NT) {
+        const int e = magic_div(it, m_upg, UPG), j = it - e * UPG;
+        if (only && !only[e]) continue;
+        const int pq = magic_div(j, m_upp, UPP), ch = j - pq * UPP, pl = pq >= P ? 1 : 0, q = pq - pl * P;
+        uint32_t o[Enc4<OD>::WORDS];
+        if (CP && q == LP) Enc4<OD>::fill(p.const_plane, o);
+        else Enc4<OD>::run(smtab[pl * 3 + q], cell_selector(*(const uint32_t*)(tile + e * C + ch * 4)), o);
+        char* dst = obase + (size_t)it * UB;
+        if constexpr (Enc4<OD>::WORDS == 4) st_cs((uint4*)dst, make_uint4(o[0], o[1 % Enc4<OD>::WORDS], o[2 % Enc4<OD>::WORDS], o[3 % Enc4<OD>::WORDS]));
+        else if constexpr (Enc4<OD>::WORDS == 2) st_cs((uint2*)dst, make_uint2(o[0], o[1 % Enc4<OD>::WORDS]));
+        else *(uint32_t*)dst = o[0];
+    }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------
 // C_T: cells per env at compile time (0 = runtime), NT threads, OD obs dtype, LP lut planes (0 = no obs),
 // CP const plane, CH cells per encode item (8, 4 or 1; C % CH == 0), MODE.
@@ -190,7 +218,9 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
     uint64_t* bar = (uint64_t*)(((uintptr_t)(rflag + G) + 7) & ~(uintptr_t)7);
     PlaneTab* smtab = (PlaneTab*)(((uintptr_t)(bar + 1) + 15) & ~(uintptr_t)15);  // [2][3] tables of the linear schedule (10x10 only)
     constexpr bool kLinear = C_T == 144 && LP > 0;
-    if (kLinear && tid < 6) smtab[tid] = p.tab[tid / 3][tid % 3];  // visible after the first __syncthreads below
+    // small boards of any other size: the unit-of-4-cells linear schedule (large grids keep the per-plane one: their planes are long runs)
+    const bool linear4 = C_T == 0 && LP > 0 && (C & 3) == 0 && C < 1024 && !(p.variant & 8);
+    if ((kLinear || linear4) && tid < 6) smtab[tid] = p.tab[tid / 3][tid % 3];  // visible after the first __syncthreads below
 
     const int8_t* gsrc = p.grid + env0 * C;
     const uint32_t tile_bytes = (uint32_t)(nG * C);
@@ -257,6 +287,7 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
             __syncthreads();
             if (LP > 0 && MODE == MODE_STEP && p.obs_term) {  // last frame of the games that just finished, before they are rebuilt
                 if constexpr (kLinear) encode_tile_linear144<NT, OD, LP, CP>(tile, nG, env0, p, p.obs_every_tick ? t : 0, smtab, p.obs_term, rflag);
+                else if (linear4) encode_tile_linear4<NT, OD, LP, CP>(tile, C, nG, env0, p, p.obs_every_tick ? t : 0, smtab, p.obs_term, rflag);
                 else encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, p.obs_every_tick ? t : 0, p.obs_term, rflag);
                 __syncthreads();
             }
@@ -328,6 +359,8 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
             if constexpr (kLinear) {  // one contiguous 512-byte run per warp store (see step_bits.cu); TRON_OPT_ENCODE_VARIANT 8 = per-plane schedule
                 if (!(p.variant & 8)) encode_tile_linear144<NT, OD, LP, CP>(tile, nG, env0, p, tt, smtab);
                 else encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, tt);
+            } else if (linear4) {
+                encode_tile_linear4<NT, OD, LP, CP>(tile, C, nG, env0, p, tt, smtab);
             } else {
                 encode_tile<C_T, NT, OD, LP, CP, CH>(tile, nG, env0, p, tt);
             }

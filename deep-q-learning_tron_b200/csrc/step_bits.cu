@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kBitsThreads) step_bits_kernel(const StepParam
     // store schedule: linear (one contiguous 512-byte run per warp store) on the 10x10 board; TRON_OPT_ENCODE_VARIANT 8 selects the
     // per-plane schedule of encode_tile() for comparison
     const bool linear = W_T == 10 && !(p.variant & 8);
-    const bool linear4 = W_T == 0 && (C & 3) == 0 && !(p.variant & 8);  // other boards: units of 4 cells (step_kernels.cuh)
+    const bool linear4 = W_T == 0 && LP == 3 && (C & 3) == 0 && C <= 256 && !(p.variant & 8);  // other boards, pop_up planes: units of 4 cells (step_kernels.cuh)
     if (LP > 0 && (linear || linear4)) {
         if (tid < 6) smtab[tid] = p.tab[tid / 3][tid % 3];
         __syncthreads();

@@ -218,8 +218,9 @@ __global__ void __launch_bounds__(NT) step_tile_kernel(const StepParams p) {
     uint64_t* bar = (uint64_t*)(((uintptr_t)(rflag + G) + 7) & ~(uintptr_t)7);
     PlaneTab* smtab = (PlaneTab*)(((uintptr_t)(bar + 1) + 15) & ~(uintptr_t)15);  // [2][3] tables of the linear schedule (10x10 only)
     constexpr bool kLinear = C_T == 144 && LP > 0;
-    // small boards of any other size: the unit-of-4-cells linear schedule (large grids keep the per-plane one: their planes are long runs)
-    const bool linear4 = C_T == 0 && LP > 0 && (C & 3) == 0 && C < 1024 && !(p.variant & 8);
+    // other small boards with pop_up planes: the unit-of-4-cells linear schedule (measured at 8x8: pop_up 0.79 -> 0.86; one-plane
+    // encodings and boards from 12x12 up are faster with the per-plane schedule, whose stores are twice as wide)
+    const bool linear4 = C_T == 0 && LP == 3 && (C & 3) == 0 && C <= 256 && !(p.variant & 8);
     if ((kLinear || linear4) && tid < 6) smtab[tid] = p.tab[tid / 3][tid % 3];  // visible after the first __syncthreads below
 
     const int8_t* gsrc = p.grid + env0 * C;

@@ -261,6 +261,7 @@ def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloa
     else:
         obs = env.reset() if not resume else env.observe()
     events = []
+    sample_bufs = None
     n_learn = 0
     last_stats = env.stats_dict()
     batch = agent.memory.batch_size
@@ -283,7 +284,8 @@ def train(n_envs=65536, env_steps=64, device=None, seed=0, obs_dtype=torch.bfloa
         agent.learn_finish()  # the learn step begun last tick: its all-reduce ran behind this tick's forward + env step
         have = len(frames) if frames is not None else len(agent.memory)
         if (t + 1) % learn_every == 0 and have > batch:
-            exp = frames.sample(batch) if frames is not None else agent.memory.sample()
+            # the sampled batch is consumed by backward before the next learn step, so its buffers are reused
+            exp = sample_bufs = (frames.sample(batch, out=sample_bufs) if frames is not None else agent.memory.sample())
             n_learn += 1
             if overlap:
                 agent.learn_begin(exp)

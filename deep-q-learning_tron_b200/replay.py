@@ -109,13 +109,16 @@ class ReplayRing:
         return (s, torch.empty((k, 1), dtype=torch.int64, device=self.device), torch.empty((k, 1), dtype=torch.float32, device=self.device),
                 torch.empty_like(s), torch.empty((k, 1), dtype=torch.float32, device=self.device))
 
-    def sample(self, k, out_dtype=torch.float32, counter=None, want_indices=False):
-        """k distinct transitions, uniformly (random.sample, DDQN.py:191-200), sampled and gathered in ONE launch."""
+    def sample(self, k, out_dtype=torch.float32, counter=None, want_indices=False, out=None):
+        """k distinct transitions, uniformly (random.sample, DDQN.py:191-200), sampled and gathered in ONE launch.
+        out: the 5-tuple a previous call returned, to write into the same tensors again (saves five allocations per batch)."""
         if counter is None:
             counter, self.sample_counter = self.sample_counter, self.sample_counter + 1
         if not 0 < k <= len(self):
             raise ValueError("sample: need 0 < k <= len(ring)=%d, got %d" % (len(self), k))
-        s, a, r, s2, d = self._outputs(k, out_dtype)
+        s, a, r, s2, d = out[:5] if out is not None else self._outputs(k, out_dtype)
+        if out is not None and (s.shape[0] != k or s.dtype != out_dtype or tuple(s.shape[1:]) != self.frame_shape):
+            raise ValueError("sample: `out` does not match k / out_dtype / the frame shape")
         idx = torch.empty(k, dtype=torch.int64, device=self.device) if want_indices else None
         with _OnDevice(self.device):
             _lib.check(self.lib.replay_sample_gather(C.byref(self.ring), len(self), k, self.seed, counter, s.data_ptr(), s2.data_ptr(),
@@ -189,8 +192,9 @@ class FrameRing:
         self.tick = t + 1
         return res
 
-    def sample(self, k, out_dtype=torch.float32, counter=None, want_indices=False):
-        """k distinct complete transitions, uniformly, one launch -> (s, a i64 [k,1], r f32 [k,1], s', d f32 [k,1])"""
+    def sample(self, k, out_dtype=torch.float32, counter=None, want_indices=False, out=None):
+        """k distinct complete transitions, uniformly, one launch -> (s, a i64 [k,1], r f32 [k,1], s', d f32 [k,1]).
+        out: the 5-tuple a previous call returned, to write into the same tensors again (saves five allocations per batch)."""
         n_ticks = min(self.tick, self.S - 1)
         if counter is None:
             counter, self.sample_counter = self.sample_counter, self.sample_counter + 1
@@ -198,11 +202,16 @@ class FrameRing:
             raise ValueError("sample: need 0 < k <= %d complete transitions, got %d" % (n_ticks * self.rows, k))
         if out_dtype not in (torch.float32, torch.bfloat16):
             raise ValueError("out_dtype must be float32 or bfloat16")
-        s = torch.empty((k,) + self.frame_shape, dtype=out_dtype, device=self.device)
-        s2 = torch.empty_like(s)
-        a = torch.empty((k, 1), dtype=torch.int64, device=self.device)
-        r = torch.empty((k, 1), dtype=torch.float32, device=self.device)
-        d = torch.empty((k, 1), dtype=torch.float32, device=self.device)
+        if out is not None:
+            s, a, r, s2, d = out[:5]
+            if s.shape[0] != k or s.dtype != out_dtype or tuple(s.shape[1:]) != self.frame_shape:
+                raise ValueError("sample: `out` does not match k / out_dtype / the frame shape")
+        else:
+            s = torch.empty((k,) + self.frame_shape, dtype=out_dtype, device=self.device)
+            s2 = torch.empty_like(s)
+            a = torch.empty((k, 1), dtype=torch.int64, device=self.device)
+            r = torch.empty((k, 1), dtype=torch.float32, device=self.device)
+            d = torch.empty((k, 1), dtype=torch.float32, device=self.device)
         idx = torch.empty(k, dtype=torch.int64, device=self.device) if want_indices else None
         with _OnDevice(self.device):
             _lib.check(self.lib.replay_frames_sample_gather(C.byref(self.fr), self.tick - n_ticks, n_ticks, k, self.seed, counter, s.data_ptr(),

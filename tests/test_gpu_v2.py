@@ -117,6 +117,12 @@ def test_sample_gather_one_launch_matches_oracle(dt, F):
         for gg, ww in zip((s, a, r, s2, d), want):
             assert np.array_equal(to_np(gg).reshape(ww.shape), ww)
     assert sorted(ring.sample_indices(cap, counter=9).cpu().numpy().tolist()) == list(range(cap))
+    a = ring.sample(64, counter=11)
+    b = ring.sample(64, counter=12)
+    again = ring.sample(64, counter=11, out=b)  # same tensors, new content
+    assert again[0].data_ptr() == b[0].data_ptr() and all(torch.equal(x, y) for x, y in zip(a, again))
+    with pytest.raises(ValueError):
+        ring.sample(32, out=b)
 
 
 def test_sampler_is_uniform_over_sizes_that_are_not_powers_of_two():

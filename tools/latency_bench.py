@@ -74,7 +74,10 @@ def main():
         for k in (64, 4096):
             for name, obj in (("ReplayRing.sample", ring), ("FrameRing.sample", fr)):
                 fn = lambda: obj.sample(k)
-                out.append(dict(op=name, k=k, planes=planes, dtype=str(dt), wall_us_per_call=wall_us(fn), device_us_per_launch=device_us(fn)))
+                bufs = obj.sample(k)
+                fn2 = lambda: obj.sample(k, out=bufs)
+                out.append(dict(op=name, k=k, planes=planes, dtype=str(dt), wall_us_per_call=wall_us(fn), wall_us_per_call_reusing_outputs=wall_us(fn2),
+                                device_us_per_launch=device_us(fn)))
         del ring, fr, env
         torch.cuda.empty_cache()
     for o in out:

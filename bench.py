@@ -543,15 +543,15 @@ def run_ours(a):
         import DQN
         # #3: DQN.py survivor loop, 65,536 self-play envs on each GPU (independent replicas), frame-sharing GPU replay
         tm3 = {}
-        DQN.train(n_envs=65536, iterations=1, device=dev, seed=rank)  # warm-up (cuDNN autotune, allocator)
+        DQN.train(n_envs=65536, iterations=1, device=dev, seed=rank, amp=True)  # warm-up (cuDNN autotune, allocator)
         torch.cuda.synchronize(); barrier()
-        DQN.train(n_envs=65536, iterations=2, device=dev, seed=rank, timings=tm3)
+        DQN.train(n_envs=65536, iterations=2, device=dev, seed=rank, timings=tm3, amp=True)
         tot3 = max_over_ranks(tm3["q_forward_ms"] + tm3["env_replay_ms"] + tm3["learn_ms"])
         configs["cfg3"] = {"workload": "BASELINE config #3: DQN.py survivor loop, 65,536 batched self-play envs per GPU, 1-plane f32 observations, frame-sharing GPU replay",
                            "value": world * 65536 * tm3["ticks"] / (tot3 * 1e-3), "unit": UNIT, "n_gpus": world, "ticks": tm3["ticks"], "learn_steps": tm3["learn_steps"],
                            "ms": {"q_forward": max_over_ranks(tm3["q_forward_ms"]), "env_replay": max_over_ranks(tm3["env_replay_ms"]), "learn": max_over_ranks(tm3["learn_ms"])},
                            "env_replay_fraction_of_loop": tm3["env_replay_ms"] / (tm3["q_forward_ms"] + tm3["env_replay_ms"] + tm3["learn_ms"]),
-                           "state_layout": tm3["layout"], "replay": tm3["replay"]}
+                           "acting_forward": "bf16 autocast", "state_layout": tm3["layout"], "replay": tm3["replay"]}
         # #4: DDQN.py, 131,072 envs per GPU (1M over 8 GPUs), pop_up 3-plane bf16 observations, NCCL all-reduce of the Q-net gradient
         tm4 = {}
         DDQN.train(n_envs=131072, env_steps=8, device=dev, seed=0, amp=True)  # warm-up

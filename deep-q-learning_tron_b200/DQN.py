@@ -96,14 +96,15 @@ def learn_step(model, optimizer, batch):
 
 
 def train(model=None, n_envs=4096, iterations=100, learn_steps_per_iter=1, device="cuda", seed=0, log=None, layout="auto", replay="frames",
-          save_every=0, save_dir="save", on_cycle=None, timings=None):
+          save_every=0, save_dir="save", on_cycle=None, timings=None, amp=False):
     """Batched restatement of DQN.train (DQN.py:135-309): self-play with the survivor reward (step index / 100 / -25 / 0),
     1-plane observations, one smooth-L1 learn step per cycle on a uniform sample, target r or r + gamma * max Q(s').
 
     replay="frames": the tick kernel fills a frame-sharing ring (no push); "ring": explicit transitions through replay_push.
     save_every: write the reference's checkpoint (save/DQN.bak, DQN.py:295) every that many cycles.
     on_cycle(cycle, stats): the numbers the reference logs per cycle (DQN.py:296-306): loss, p1 win rate, mean duration.
-    timings: optional dict receiving device times in ms summed over all ticks (q_forward, env_replay, learn)."""
+    timings: optional dict receiving device times in ms summed over all ticks (q_forward, env_replay, learn).
+    amp: run the ACTING forward under bf16 autocast (the learn step stays fp32 like the reference)."""
     import os
     from Net.DQNNet import Net
     from tron_b200.replay import FrameRing
@@ -127,7 +128,11 @@ def train(model=None, n_envs=4096, iterations=100, learn_steps_per_iter=1, devic
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
             with torch.no_grad():
-                q = model(obs.view(rows, 1, 12, 12))
+                if amp:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        q = model(obs.view(rows, 1, 12, 12)).float()
+                else:
+                    q = model(obs.view(rows, 1, 12, 12))
             ev[1].record()
             if frames is not None:
                 env.select_actions(q, epsilon, counter=env.counter, out=frames.actions_slot().view(-1))

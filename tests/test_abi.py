@@ -45,6 +45,8 @@ def test_struct_layout_matches_header():
              offsetof(tron_step_args, reward_table), offsetof(tron_step_args, seed), offsetof(tron_step_args, slide_tape),
              offsetof(tron_step_args, stats), offsetof(tron_step_args, n_ticks));
       printf("%zu %zu\n", offsetof(replay_ring, capacity), offsetof(replay_ring, done));
+      printf("%zu %zu %zu %zu %zu %zu\n", sizeof(replay_frames), offsetof(replay_frames, rows), offsetof(replay_frames, frames), offsetof(replay_frames, done),
+             offsetof(tron_step_args, obs_terminal), offsetof(tron_step_args, extra));
       return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "p.c"), "w").write(prog)
@@ -55,7 +57,9 @@ def test_struct_layout_matches_header():
     assert v[:4] == [C.sizeof(S), C.sizeof(R), 8, C.sizeof(abi.Reward)]
     assert v[4:12] == [S.state.offset, S.obs.offset, S.lut.offset, S.reward_table.offset, S.seed.offset, S.slide_tape.offset,
                        S.stats.offset, S.n_ticks.offset]
-    assert v[12:] == [R.capacity.offset, R.done.offset]
+    assert v[12:14] == [R.capacity.offset, R.done.offset]
+    F = abi.ReplayFrames
+    assert v[14:] == [C.sizeof(F), F.rows.offset, F.frames.offset, F.done.offset, S.obs_terminal.offset, S.extra.offset]
 
 
 def test_geometry_helpers_host_only(lib):

@@ -119,8 +119,10 @@ def dtype_size(dt):
 
 def state_bytes(n_envs, width, height, layout=LAYOUT_TILE8):
     per = 32 if layout == LAYOUT_BITS10 else 48 if layout == LAYOUT_BITS else cells_per_env(width, height)
-    if layout == LAYOUT_TRAIL:  # 64 hot bytes (header + 12 list words) + the cold tail of the lists
+    if layout == LAYOUT_TRAIL:  # 64 hot bytes (header + 12 list words) + the cold tail of the lists + the bitmap of the cells it names
         per = 64 + ((4 * max(0, width * height - 12) + 15) & ~15)
+        if width * height > 12:
+            per += (4 * width * ((height + 31) >> 5) + 15) & ~15
     grid = (n_envs * per + 255) & ~255
     meta = (8 * n_envs + 255) & ~255
     return grid + meta + 8 * n_envs

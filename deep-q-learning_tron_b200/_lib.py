@@ -10,7 +10,8 @@ from . import _abi as abi
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # TRON_B200_DEBUG=1 selects the range-checked build (libtron_b200_debug.so, tests only)
 DEBUG = os.environ.get("TRON_B200_DEBUG", "0") == "1"
-LIB_PATH = os.path.join(_HERE, "libtron_b200_debug.so" if DEBUG else "libtron_b200.so")
+# TRON_B200_LIB=<path> loads another build of the same ABI (A/B measurements of kernel changes; tools only)
+LIB_PATH = os.environ.get("TRON_B200_LIB") or os.path.join(_HERE, "libtron_b200_debug.so" if DEBUG else "libtron_b200.so")
 
 
 class TronError(RuntimeError):

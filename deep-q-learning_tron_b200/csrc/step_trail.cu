@@ -14,7 +14,12 @@
 // them.  A tick of thread-per-game is then four fully coalesced 512-byte warp loads, one coalesced header store and one
 // coalesced store of the uint4 that received this tick's entries: the kernel streams at HBM bandwidth instead of paying one
 // DRAM row activation per game (round 1 kept a game's record contiguous, 16 KB apart from its neighbours: 0.34 of peak).
-// Only episodes longer than 12 ticks touch the cold area.  Unused entries of the hot words hold the impossible key 0xFFFF (see
+// Only episodes longer than 12 ticks touch the cold area, which holds two things per game: the list words >= 12 (write-only for
+// the tick: they give export / observation rendering the owner and slide flag of every cell) and an OCCUPANCY BITMAP over the
+// interior cells with one bit per cell that a cold entry names.  "Is this cell free?" for a long game is then the 12-word register
+// scan plus ONE 4-byte probe of the bitmap instead of a walk over the whole list (round 2 walked it: every probe of a long
+// game cost O(episode length) loads, the epsilon-greedy streams ran at a ninth of the short-episode rate); a reset zeroes only the
+// bitmap words that the finished game's cold entries name.  Unused entries of the hot words hold the impossible key 0xFFFF (see
 // TrailCells), which makes "is this cell free?" a branch-free packed-minimum over the words (VIMNMX3.U16x2, 1.5 instructions per
 // list word); the kernel is instruction-issue-bound, not bandwidth-bound (profiles/r2_step_trail_64x64_2M.json: issue active 75 %,
 // DRAM 29 %), so instruction count is what the layout and these tricks buy.
@@ -26,10 +31,14 @@ namespace tron {
 constexpr int kTrailThreads = 128;
 constexpr int kTrailHot = 12;  // list words held in the hot arrays / in registers (entries 0..11 of both players)
 
-__host__ __device__ inline int trail_cold_words(int W, int H) {
+// cold area of a game: list words 12.. (lw words), then the occupancy bitmap of the cells those words name (W rows of wpr words)
+__host__ __device__ inline int trail_list_words(int W, int H) {
     const int n = W * H - kTrailHot;
     return n <= 0 ? 0 : ((n + 3) & ~3);
 }
+__host__ __device__ inline int trail_bitmap_wpr(int H) { return (H + 31) >> 5; }
+__host__ __device__ inline int trail_bitmap_words(int W, int H) { return W * H <= kTrailHot ? 0 : ((W * trail_bitmap_wpr(H) + 3) & ~3); }
+__host__ __device__ inline int trail_cold_words(int W, int H) { return trail_list_words(W, H) + trail_bitmap_words(W, H); }
 size_t trail_game_bytes_host(int W, int H) { return 64u + 4u * (size_t)trail_cold_words(W, H); }
 
 // address of list word k of the game at dense index i
@@ -37,7 +46,8 @@ struct TrailStore {
     uint4* hot;
     uint32_t* cold;
     long long SN;  // games in the arrays
-    int cw;        // cold words per game
+    int cw;        // cold words per game (list words 12.. + bitmap)
+    int lw;        // of which list words
     __device__ __forceinline__ uint32_t* word(long long i, int k) const {
         return k < kTrailHot ? ((uint32_t*)(hot + (long long)(1 + (k >> 2)) * SN + i) + (k & 3)) : (cold + i * cw + (k - kTrailHot));
     }
@@ -47,6 +57,7 @@ __host__ __device__ inline TrailStore trail_store(const StepParams& p) {
     s.hot = (uint4*)p.grid;
     s.SN = p.state_N;
     s.cw = trail_cold_words(p.W, p.H);
+    s.lw = trail_list_words(p.W, p.H);
     s.cold = (uint32_t*)((char*)p.grid + 64ull * (unsigned long long)p.state_N);
     return s;
 }
@@ -63,11 +74,31 @@ struct TrailCells {
     // impossible key 0xFFFF, so that get() needs no validity test per entry.  Whoever empties a list (reset, auto-reset, import)
     // writes the placeholders back; the cold words (positions >= 12) carry no such guarantee and are tested against n.
     uint32_t hot[kTrailHot];
-    uint32_t* cold;           // this game's cold words (list words 12..)
+    uint32_t* cold;           // this game's cold words: list words 12.., then the occupancy bitmap of the cells they name
     int n0, n1;               // entries per player at the start of the tick (those are in hot[] / cold[])
     uint32_t fb, fs;          // entries appended during this tick: bodies {P1 | P2 << 16} and slide tiles, 0xFFFF = none
     int W, H;
     unsigned dirty;           // bit q: hot uint4 q changed
+
+    __device__ __forceinline__ uint32_t* bmp() const { return cold + trail_list_words(W, H); }
+    __device__ __forceinline__ int wpr() const { return trail_bitmap_wpr(H); }
+    // a cold entry was appended: its cell goes into the bitmap
+    __device__ __forceinline__ void mark(uint32_t entry) {
+        const int r = (int)(entry & 0x7Fu), c = (int)((entry >> 8) & 0xFFu);
+        const int w = r * wpr() + (c >> 5);
+        if (!TRON_DCHECK(r < W && c < H && w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) return;
+        atomicOr(bmp() + w, 1u << (c & 31));  // result unused -> RED.OR: no load the tick would have to wait for
+    }
+    // the finished game's cold entries name the only bitmap words that can hold set bits: zero those (O(episode length), no extra state)
+    __device__ __forceinline__ void unmark_all() {
+        uint32_t* b = bmp();
+        const int nmax = max(n0, n1);
+        for (int k = kTrailHot; k < nmax; ++k) {
+            const uint32_t v = cold[k - kTrailHot];
+            if (k < n0) { const int w = (int)(v & 0x7Fu) * wpr() + (int)((v >> 13) & 7u); if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) b[w] = 0u; }
+            if (k < n1) { const int w = (int)((v >> 16) & 0x7Fu) * wpr() + (int)(v >> 29); if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) b[w] = 0u; }
+        }
+    }
 
     __device__ __forceinline__ static unsigned short pack(int r, int c, bool slide) { return (unsigned short)((r & 0x7F) | (slide ? 0x80 : 0) | (c << 8)); }
 
@@ -79,8 +110,17 @@ struct TrailCells {
     __device__ __forceinline__ void clear() {  // fresh game: empty lists; the hot uint4s that held entries go back as placeholders
         const int used = min(kTrailHot, max(n0, n1));
         dirty |= (used > 0 ? 2u : 0u) | (used > 4 ? 4u : 0u) | (used > 8 ? 8u : 0u);
+        unmark_all();
         n0 = n1 = 0; fb = fs = 0xFFFFFFFFu;
         blank();
+    }
+    // explicit reset: establishes every invariant whatever the memory held before (placeholders in all hot words, empty bitmap)
+    __device__ __forceinline__ void reset_all() {
+        uint32_t* b = bmp();
+        for (int w = 0; w < trail_bitmap_words(W, H); ++w) b[w] = 0u;
+        n0 = n1 = 0; fb = fs = 0xFFFFFFFFu;
+        blank();
+        dirty = 0xEu;
     }
 
     __device__ __forceinline__ int get(int r, int c) const {
@@ -92,10 +132,9 @@ struct TrailCells {
 #pragma unroll
         for (int w = 0; w < kTrailHot; w += 2) acc = __vimin3_u16x2(acc, (hot[w] & 0xFF7FFF7Fu) ^ key2, (hot[w + 1] & 0xFF7FFF7Fu) ^ key2);
         uint32_t hit = zero_halves(acc);
-        const int nmax = max(n0, n1);
-        for (int w = kTrailHot; w < nmax; ++w) {  // long episode: the rest of the lists, straight from memory
-            const uint32_t z = zero_halves((cold[w - kTrailHot] & 0xFF7FFF7Fu) ^ key2);
-            hit |= z & ((w < n0 ? 0x00008000u : 0u) | (w < n1 ? 0x80000000u : 0u));
+        if (max(n0, n1) > kTrailHot) {  // long episode: the cells of the list entries 12.. are in the bitmap
+            const int w = r * wpr() + (c >> 5);
+            if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) hit |= (bmp()[w] >> (c & 31)) & 1u;
         }
         return hit ? TRON_TILE_P1_BODY : TRON_TILE_EMPTY;  // callers only test for EMPTY
     }
@@ -118,6 +157,7 @@ struct TrailCells {
             dirty |= 1u << (1 + (k >> 2));
         } else {
             ((unsigned short*)(cold + (k - kTrailHot)))[owner] = (unsigned short)entry;
+            mark(entry);
         }
     }
     // append this tick's entries to the lists (registers for list words < 12, memory beyond): per player the body, then the slide tile
@@ -133,6 +173,8 @@ struct TrailCells {
                     dirty |= 1u << (1 + (k >> 2));
                 } else {
                     cold[k - kTrailHot] = fb;
+                    mark(fb & 0xFFFFu);
+                    mark(fb >> 16);
                 }
             }
             n0 = n1 = k + 1;
@@ -187,8 +229,8 @@ __global__ void __launch_bounds__(kTrailThreads, 8) step_trail_kernel(const Step
         BoxRegs bx;
         const bool do_reset = env_tick<MODE, false, FEAT>(g, p, e, env, t, tid, bx);
         if (do_reset) {
-            g.clear();
-            if (MODE == MODE_RESET) g.dirty = 0xEu;  // an explicit reset establishes the invariant whatever the memory held before
+            if (MODE == MODE_RESET) g.reset_all();
+            else g.clear();
         } else {
             g.commit();
         }
@@ -424,12 +466,17 @@ __global__ void trail_import_kernel(const StepParams p, const int8_t* __restrict
         const int Hc = H + 2;
         for (int q = 1; q <= 3; ++q) st.hot[(long long)q * st.SN + i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);  // invariant: unused = 0xFFFF
         const int8_t* t = tiles + (size_t)env * (W + 2) * (H + 2);
+        uint32_t* bmp = st.cold + i * st.cw + st.lw;
+        const int wpr = trail_bitmap_wpr(H);
+        for (int w = 0; w < trail_bitmap_words(W, H); ++w) bmp[w] = 0u;
         int n1 = 0, n2 = 0;
         for (int r = 0; r < W; ++r)
             for (int c = 0; c < H; ++c) {
                 const int v = t[(r + 1) * Hc + c + 1];
-                if (v == TRON_TILE_P1_BODY || v == TRON_TILE_P1_SLIDE) ((unsigned short*)st.word(i, n1++))[0] = TrailCells::pack(r, c, v == TRON_TILE_P1_SLIDE);
-                else if (v == TRON_TILE_P2_BODY || v == TRON_TILE_P2_SLIDE) ((unsigned short*)st.word(i, n2++))[1] = TrailCells::pack(r, c, v == TRON_TILE_P2_SLIDE);
+                int k = -1;
+                if (v == TRON_TILE_P1_BODY || v == TRON_TILE_P1_SLIDE) ((unsigned short*)st.word(i, k = n1++))[0] = TrailCells::pack(r, c, v == TRON_TILE_P1_SLIDE);
+                else if (v == TRON_TILE_P2_BODY || v == TRON_TILE_P2_SLIDE) ((unsigned short*)st.word(i, k = n2++))[1] = TrailCells::pack(r, c, v == TRON_TILE_P2_SLIDE);
+                if (k >= kTrailHot) bmp[r * wpr + (c >> 5)] |= 1u << (c & 31);  // a cold entry: its cell is looked up through the bitmap
             }
         hdr.z = (uint32_t)n1 | ((uint32_t)n2 << 16);
         uint32_t packed;

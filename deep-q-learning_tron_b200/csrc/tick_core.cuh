@@ -141,6 +141,8 @@ struct LoggedByteCells {
 // FEAT: which optional paths are compiled in -- FEAT_SLIDE the ice/temper slide modes, FEAT_EPS the epsilon-greedy proxy policy.  A
 // launcher picks the leanest instantiation the call allows (fewer instructions and registers for the plain tick).
 enum : int { FEAT_SLIDE = 1, FEAT_EPS = 2, FEAT_ALL = 3 };
+static_assert(TRON_STAT_EPISODES == 0 && TRON_STAT_P1_WINS == 1 && TRON_STAT_P2_WINS == 2 && TRON_STAT_DRAWS == 3 && TRON_STAT_EP_TICKS == 4 &&
+              TRON_STAT_BAD_ACTION == 5 && TRON_STAT_ENV_STEPS == 6, "env_tick's lane-per-field statistics rely on this field order");
 template <int MODE, bool TRACK, int FEAT = FEAT_ALL, class Cells>
 __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState& e, long long env, int t, int tid, BoxRegs& bx,
                                          const int* pre_actions = nullptr) {
@@ -268,6 +270,19 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
         if (p.eplen) p.eplen[tn] = fin;
         if (p.stats) {  // warp-aggregated counters, striped over TRON_STATS_SLOTS rows
             const unsigned am = __activemask();
+            if (am == 0xFFFFFFFFu) {
+                // full warp: every lane's five 0/1 contributions are summed in ONE packed reduction (6-bit fields, a warp sums to at
+                // most 32 per field) and lane k adds field k of the stripe -- one RED instruction for the warp instead of seven
+                const bool f = fin > 0;
+                const unsigned contrib = (f && winner == 1 ? 1u : 0u) | (f && winner == 2 ? 1u << 6 : 0u) | (f && winner == 0 ? 1u << 12 : 0u) |
+                                         (bad ? 1u << 18 : 0u) | (stepped ? 1u << 24 : 0u);
+                const unsigned sum = __reduce_add_sync(0xFFFFFFFFu, contrib);
+                const unsigned ticks = __reduce_add_sync(0xFFFFFFFFu, (unsigned)fin);
+                const int lane = tid & 31;  // fields: 0 episodes, 1 P1 wins, 2 P2 wins, 3 draws, 4 episode ticks, 5 bad actions, 6 env steps
+                const unsigned w1 = sum & 63u, w2 = (sum >> 6) & 63u, dr = (sum >> 12) & 63u;
+                const unsigned v = lane == 0 ? w1 + w2 + dr : lane == 4 ? ticks : (sum >> (6 * (lane - (lane < 4 ? 1 : 2)))) & 63u;
+                if (lane < 7 && v) atomicAdd(p.stats + (size_t)(blockIdx.x % TRON_STATS_SLOTS) * TRON_STATS_FIELDS + lane, (unsigned long long)v);
+            } else {
             const unsigned m_fin = __ballot_sync(am, fin > 0), m_w1 = __ballot_sync(am, fin > 0 && winner == 1),
                            m_w2 = __ballot_sync(am, fin > 0 && winner == 2), m_bad = __ballot_sync(am, bad), m_step = __ballot_sync(am, stepped);
             const unsigned ticks = __reduce_add_sync(am, (unsigned)fin);
@@ -282,6 +297,7 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
                 }
                 if (m_bad) atomicAdd(s + TRON_STAT_BAD_ACTION, (unsigned long long)__popc(m_bad));
                 atomicAdd(s + TRON_STAT_ENV_STEPS, (unsigned long long)__popc(m_step));
+            }
             }
         }
     }

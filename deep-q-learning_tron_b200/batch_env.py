@@ -19,7 +19,7 @@ _ENC_OF = {"none": abi.ENC_NONE, "lut1": abi.ENC_LUT1, "popup3": abi.ENC_POPUP3,
 _LAYOUT_OF = {"tile8": abi.LAYOUT_TILE8, "bits10": abi.LAYOUT_BITS10, "trail": abi.LAYOUT_TRAIL, "bits": abi.LAYOUT_BITS}
 
 
-def auto_layout(width, height, obs_enc, slide_mode):
+def auto_layout(width, height, obs_enc, slide_mode, obs_dtype=torch.bfloat16):
     """fastest state layout that can represent a configuration (all layouts are bit-identical through the API)"""
     enc_none = obs_enc in ("none", abi.ENC_NONE)
     no_slide = slide_mode in (None, abi.SLIDE_NONE)
@@ -27,7 +27,15 @@ def auto_layout(width, height, obs_enc, slide_mode):
         return "bits10"
     if width == 10 and height == 10:
         return "bits"   # config.py's board with a slide mode (GAME_MODE="temper"): three bit planes
-    if enc_none and (width + 2) * (height + 2) >= 1024:
+    cells = (width + 2) * (height + 2)
+    if enc_none:
+        return "trail" if cells >= 1024 else "tile8"
+    # fused observations on boards from 20x20 up: the trail lists with bulk-stored template rows beat the int8 grid (no grid
+    # traffic at all; profiles/r2_large_obs.jsonl) wherever that kernel applies (observation rows of a multiple of 16 bytes)
+    enc = _ENC_OF[obs_enc] if isinstance(obs_enc, str) else int(obs_enc)
+    es = abi.dtype_size(_CODE_OF[obs_dtype] if isinstance(obs_dtype, torch.dtype) else int(obs_dtype))
+    row = 2 * abi.enc_planes(enc) * cells * es
+    if width * height >= 400 and width <= 126 and height <= 126 and cells % 4 == 0 and row % 16 == 0 and row <= 200 * 1024:
         return "trail"
     return "tile8"
 _SLIDE_OF = {None: abi.SLIDE_NONE, "tape": abi.SLIDE_TAPE, "ice": abi.SLIDE_ICE, "temper": abi.SLIDE_TEMPER}
@@ -86,7 +94,7 @@ class BatchedTron:
         _lib.require_cuda()
         self.lib = _lib.load()
         if layout == "auto":
-            layout = auto_layout(width, height, obs_enc, slide_mode)
+            layout = auto_layout(width, height, obs_enc, slide_mode, obs_dtype)
         self.layout = _LAYOUT_OF[layout] if isinstance(layout, str) else int(layout)
         self.spawn_mode = {"uniform": abi.SPAWN_UNIFORM, "fair": abi.SPAWN_FAIR}[spawn_mode] if isinstance(spawn_mode, str) else int(spawn_mode)
         self.policy = {"uniform": abi.POLICY_UNIFORM, "free_eps": abi.POLICY_FREE_EPS}[policy] if isinstance(policy, str) else int(policy)

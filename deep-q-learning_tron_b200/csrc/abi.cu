@@ -123,7 +123,6 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
         if (a->slide_mode == TRON_SLIDE_TAPE && !a->slide_tape) return TRON_ERR_INVALID;
         if (a->obs_terminal) {
             if (!p.obs) return TRON_ERR_INVALID;
-            if (a->layout == TRON_LAYOUT_TRAIL) return TRON_ERR_UNSUPPORTED;
             if (((uintptr_t)a->obs_terminal & 15u) != 0) return TRON_ERR_ALIGN;
             p.obs_term = a->obs_terminal;
         }

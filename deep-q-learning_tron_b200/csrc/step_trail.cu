@@ -23,6 +23,8 @@
 // TrailCells), which makes "is this cell free?" a branch-free packed-minimum over the words (VIMNMX3.U16x2, 1.5 instructions per
 // list word); the kernel is instruction-issue-bound, not bandwidth-bound (profiles/r2_step_trail_64x64_2M.json: issue active 75 %,
 // DRAM 29 %), so instruction count is what the layout and these tricks buy.
+#include <algorithm>
+
 #include "launch.h"
 #include "step_kernels.cuh"
 
@@ -374,8 +376,194 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
     }
 }
 
+// ---- fused tick + observation planes, BULK-STORE edition (the default whenever a game's observation row is a multiple of 16 B) ----
+// A game's observation row [2,P,C] equals the encoded TEMPLATE row (border WALL, interior EMPTY) except at its trail cells and
+// its two heads.  Each warp keeps one encoded template row in shared memory.  Per game it patches those few cells IN SHARED
+// MEMORY, hands the whole row to the TMA engine (cp.async.bulk shared -> global: a handful of instructions per game instead of
+// one store instruction per 16 bytes per lane, and the DRAM sees row-sized contiguous bursts), waits until the engine has READ
+// the row, and restores the patched cells.  All global observation bytes are written by the bulk engine exactly once -- there
+// are no scattered element stores to HBM and no write-ordering between the two proxies to reason about.
+template <int OD, int LP, bool CP, int MODE>
+__global__ void __launch_bounds__(kTrailThreads) step_trail_obs_bulk_kernel(const StepParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
+    constexpr int NP = LP + (CP ? 1 : 0);
+    const int C = p.C, G = p.G, Hc = p.Hc, tid = threadIdx.x, lane = tid & 31, P = p.P, warp = tid >> 5, nwarp = (int)blockDim.x >> 5;
+    const uint32_t row = 2u * (uint32_t)P * (uint32_t)C * ES;  // bytes of one game's observations; the launcher guarantees row % 16 == 0, C % 4 == 0
+    char* my = (char*)smem_raw + (size_t)warp * row;            // this warp's row buffer
+    // 1. the encoded template row: built once per CTA in warp 0's buffer, copied to the other warps' buffers
+    {
+        const int per = C / 4;
+        for (int ch = tid; ch < per; ch += (int)blockDim.x) {
+            const int c0 = ch * 4;
+            uint32_t cells = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j, r = c / Hc, q = c - r * Hc;
+                const bool wall = r == 0 || r == p.W + 1 || q == 0 || q == p.H + 1;
+                cells |= (uint32_t)(uint8_t)(int8_t)(wall ? TRON_TILE_WALL : TRON_TILE_EMPTY) << (8 * j);
+            }
+            const uint32_t sel = cell_selector(cells);
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    uint32_t o[Enc4<OD>::WORDS];
+                    if (q < LP) Enc4<OD>::run(p.tab[pl][q < LP ? q : 0], sel, o); else Enc4<OD>::fill(p.const_plane, o);
+                    uint32_t* dst = (uint32_t*)((char*)smem_raw + ((size_t)(pl * P + q) * C + (size_t)c0) * ES);
+#pragma unroll
+                    for (int w = 0; w < Enc4<OD>::WORDS; ++w) dst[w] = o[w];
+                }
+        }
+        fence_proxy_async();  // warp 0's buffer is written by every thread of the CTA: each writer orders its writes before the bulk engine's reads
+        __syncthreads();
+        if (warp > 0)
+            for (uint32_t o = (uint32_t)lane * 16u; o < row; o += 512u) *(uint4*)(my + o) = *(const uint4*)((const char*)smem_raw + o);
+        fence_proxy_async();
+        __syncthreads();  // warp 0 must not patch its buffer while the others still copy from it
+    }
+    const long long env0 = (long long)blockIdx.x * G;
+    const int nG = (int)min((long long)G, (long long)p.N - env0);
+    const int gpw = G / nwarp;
+    const int local = warp * gpw + lane;
+    const bool owner = lane < gpw && local < nG;
+    const long long env = env0 + local;
+    const TrailStore st = trail_store(p);
+    const long long gi = p.state_off + (owner ? env : env0);
+    EnvState e = unpack_meta(make_uint2(0, 0));
+    TrailCells g;
+    g.W = p.W; g.H = p.H; g.cold = st.cold + gi * st.cw;
+    g.start(0, 0);
+    g.blank();
+    if (owner) {
+        const uint4 hdr = st.hot[gi];
+        e = unpack_meta(make_uint2(hdr.x, hdr.y));
+        g.start((int)(hdr.z & 0xFFFFu), (int)(hdr.z >> 16));
+        if (MODE == MODE_STEP) g.load_hot(st, gi, kTrailHot);
+        if (MODE == MODE_OBSERVE) emit_extra(p, env);
+    }
+    // value of `tile` on plane (pl, q) written into this warp's row buffer at `cell`
+    auto patch = [&](int cell, int tile) {
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+            for (int q = 0; q < LP; ++q) store_elem<OD>(my + (size_t)(pl * P + q) * C * ES, cell, p.tab[pl][q], tile);
+    };
+    // render one game of this warp: patch the row buffer with the list entries in memory (n1 / n2 per player), the entries of the
+    // current tick that exist only in registers (fb bodies, fs slide tiles; 0xFFFF = none) and the heads; bulk-store it; restore it
+    auto render = [&](long long senv, int n1, int n2, uint32_t fb, uint32_t fs, int hr1, int hc1, int hr2, int hc2, char* dst) {
+        const long long si = p.state_off + senv;
+        const int nmax = max(n1, n2);
+        auto cell_of = [&](unsigned u) { return ((int)(u & 0x7F) + 1) * Hc + (int)(u >> 8) + 1; };
+        auto lists = [&](bool restore) {
+            for (int k = lane; k < nmax; k += 32) {
+                const uint32_t v = __ldcg(st.word(si, k));  // L2 read: another lane of this warp may have appended the entry in this tick
+#pragma unroll
+                for (int pl2 = 0; pl2 < 2; ++pl2) {
+                    if (k >= (pl2 ? n2 : n1)) continue;
+                    const unsigned u = pl2 ? (v >> 16) : (v & 0xFFFFu);
+                    const int cell = cell_of(u);
+                    if (!TRON_DCHECK(cell >= 0 && cell < C, DBG_CELL_INDEX)) continue;
+                    patch(cell, restore ? (int)TRON_TILE_EMPTY
+                                        : pl2 ? ((u & 0x80) ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY) : ((u & 0x80) ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY));
+                }
+            }
+            if (lane < 4) {  // the tick's own entries (terminal frames: the finished game's last bodies / slide tiles were never committed)
+                const uint32_t w = (lane & 1) ? fs : fb;
+                const unsigned u = (lane & 2) ? (w >> 16) : (w & 0xFFFFu);
+                if (u != 0xFFFFu) {
+                    const int cell = cell_of(u & 0xFF7Fu);
+                    if (TRON_DCHECK(cell >= 0 && cell < C, DBG_CELL_INDEX))
+                        patch(cell, restore ? (int)TRON_TILE_EMPTY
+                                            : (lane & 2) ? ((lane & 1) ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY) : ((lane & 1) ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY));
+                }
+            }
+        };
+        // -- patch: trail cells of both players (distinct cells), then the heads (P2 last, it wins a shared cell)
+        lists(false);
+        __syncwarp();
+        const int hcell1 = (hr1 + 1) * Hc + hc1 + 1, hcell2 = (hr2 + 1) * Hc + hc2 + 1;
+        if (lane == 0) { patch(hcell1, TRON_TILE_P1_HEAD); patch(hcell2, TRON_TILE_P2_HEAD); }
+        fence_proxy_async();  // every lane: its generic-proxy writes to the row become visible to the bulk engine
+        __syncwarp();
+        // -- the row leaves as bulk stores, 2 KB per lane and round
+        for (uint32_t o = (uint32_t)lane * 2048u; o < row; o += 32u * 2048u) bulk_s2g(dst + o, my + o, min(2048u, row - o));
+        bulk_commit();
+        bulk_wait_read_all();
+        __syncwarp();
+        // -- restore the template at the patched cells (trail cells are interior cells; a crashed head may sit on the border)
+        lists(true);
+        if (lane == 0) {
+            patch(hcell1, (hr1 < 0 || hc1 < 0 || hr1 >= p.W || hc1 >= p.H) ? TRON_TILE_WALL : TRON_TILE_EMPTY);
+            patch(hcell2, (hr2 < 0 || hc2 < 0 || hr2 >= p.W || hc2 >= p.H) ? TRON_TILE_WALL : TRON_TILE_EMPTY);
+        }
+        __syncwarp();
+    };
+    const int T = MODE == MODE_STEP ? p.T : 1;
+    for (int t = 0; t < T; ++t) {
+        bool fin = false;
+        int on0 = 0, on1 = 0;
+        uint32_t ofb = 0xFFFFFFFFu, ofs = 0xFFFFFFFFu;
+        if (MODE == MODE_STEP && owner) {
+            BoxRegs bx;
+            on0 = g.n0; on1 = g.n1;
+            if (env_tick<MODE_STEP, false>(g, p, e, env, t, tid, bx)) { fin = true; ofb = g.fb; ofs = g.fs; g.clear(); }
+            else g.commit();
+        }
+        if (MODE == MODE_STEP && p.obs_term) {
+            // terminal frames (tron_step_args.obs_terminal; single-tick calls only): the last frame of the games that finished in this
+            // tick and were auto-reset -- their lists as they still stand in memory, this tick's uncommitted entries, the final heads
+            unsigned m = __ballot_sync(0xFFFFFFFFu, fin);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                render(env0 + warp * gpw + src, __shfl_sync(0xFFFFFFFFu, on0, src), __shfl_sync(0xFFFFFFFFu, on1, src),
+                       __shfl_sync(0xFFFFFFFFu, ofb, src), __shfl_sync(0xFFFFFFFFu, ofs, src),
+                       __shfl_sync(0xFFFFFFFFu, e.tr1, src), __shfl_sync(0xFFFFFFFFu, e.tc1, src), __shfl_sync(0xFFFFFFFFu, e.tr2, src), __shfl_sync(0xFFFFFFFFu, e.tc2, src),
+                       (char*)p.obs_term + (size_t)(env0 + warp * gpw + src) * row);
+            }
+        }
+        if (!(MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1)) continue;
+        if (MODE == MODE_STEP && owner) g.store_dirty(st, gi);  // the whole warp reads the lists back from memory below
+        const size_t tick_off = (MODE == MODE_STEP && p.obs_every_tick) ? (size_t)t * (size_t)p.N * row : 0;
+        char* obase = (char*)p.obs + tick_off;
+        __syncwarp();  // the entries appended in this tick (plain global stores of the owning lanes) are read by the whole warp below
+        for (int src = 0; src < gpw; ++src) {  // warp-uniform loop over this warp's games
+            if (warp * gpw + src >= nG) break;
+            const long long senv = env0 + warp * gpw + src;
+            render(senv, __shfl_sync(0xFFFFFFFFu, g.n0, src), __shfl_sync(0xFFFFFFFFu, g.n1, src), 0xFFFFFFFFu, 0xFFFFFFFFu,
+                   __shfl_sync(0xFFFFFFFFu, e.r1, src), __shfl_sync(0xFFFFFFFFu, e.c1, src), __shfl_sync(0xFFFFFFFFu, e.r2, src), __shfl_sync(0xFFFFFFFFu, e.c2, src),
+                   obase + (size_t)senv * row);
+        }
+    }
+    if (MODE == MODE_STEP && owner) {
+        const uint2 m = pack_meta(e);
+        st.hot[gi] = make_uint4(m.x, m.y, (uint32_t)g.n0 | ((uint32_t)g.n1 << 16), 0u);
+    }
+}
+
+constexpr size_t kTrailBulkSmem = 200 * 1024;  // shared memory a CTA of the bulk-store kernel may use for its row buffers
+
 template <int OD, int LP, bool CP, int MODE>
 static int launch_trail_obs_one(StepParams p, cudaStream_t s) {
+    const size_t es = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
+    const size_t row = 2 * (size_t)p.P * (size_t)p.C * es;
+    if (!(p.variant & 32) && row % 16 == 0 && p.C % 4 == 0 && ((uintptr_t)p.obs & 15u) == 0 && row <= kTrailBulkSmem) {
+        // bulk-store edition: one row buffer per warp; as many warps (<= 4) and CTAs per SM as the shared memory holds
+        const int nwarp = (int)std::min<size_t>(4, kTrailBulkSmem / row);
+        const size_t smem = (size_t)nwarp * row;
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
+        // games per warp: about three waves of CTAs (the template row is built once per CTA, so few, long-lived CTAs), at most one game per lane
+        int gpw = (int)((long long)p.N / (3LL * ctas_per_sm * sm_count() * nwarp));
+        gpw = gpw < 1 ? 1 : (gpw > 32 ? 32 : gpw);
+        p.G = nwarp * gpw;
+        const unsigned grid = (unsigned)(((long long)p.N + p.G - 1) / p.G);
+        auto kernel = step_trail_obs_bulk_kernel<OD, LP, CP, MODE>;
+        if (ensure_dynamic_smem((const void*)kernel, smem) != TRON_OK) return TRON_ERR_CUDA;
+        kernel<<<grid, 32 * nwarp, smem, s>>>(p);
+        return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
+    }
+    if (p.obs_term) return TRON_ERR_UNSUPPORTED;  // terminal frames are rendered by the bulk-store kernel only
     // games per warp: aim at >= ~6 waves of CTAs (4 CTAs/SM resident), at most one game per lane
     int gpw = p.N / (6 * 4 * sm_count() * 4);
     gpw = gpw < 1 ? 1 : (gpw > 32 ? 32 : gpw);

@@ -65,7 +65,8 @@ def test_extra_side_features_follow_the_observed_game(layout):
 
 # ------------------------------------------------------------------ terminal frames
 @pytest.mark.parametrize("layout,W,dt,enc", [("tile8", 10, abi.BF16, abi.ENC_LUT1), ("bits10", 10, abi.BF16, abi.ENC_POPUP3), ("bits", 10, abi.F32, abi.ENC_LUT1),
-                                             ("bits", 7, abi.I8, abi.ENC_POPUP3_CONST), ("tile8", 20, abi.I8, abi.ENC_LUT1), ("tile8", 50, abi.BF16, abi.ENC_LUT1)])
+                                             ("bits", 7, abi.I8, abi.ENC_POPUP3_CONST), ("tile8", 20, abi.I8, abi.ENC_LUT1), ("tile8", 50, abi.BF16, abi.ENC_LUT1),
+                                             ("trail", 10, abi.BF16, abi.ENC_POPUP3), ("trail", 20, abi.F32, abi.ENC_LUT1), ("trail", 46, abi.I8, abi.ENC_POPUP3_CONST)])
 def test_obs_terminal_holds_the_last_frame_of_finished_games(layout, W, dt, enc):
     N = 1500 if W <= 20 else 200
     g, o = make_pair(N, W, W, layout=layout, obs_dtype=dt, obs_enc=enc, seed=13, const_plane=2.0)
@@ -85,10 +86,26 @@ def test_obs_terminal_holds_the_last_frame_of_finished_games(layout, W, dt, enc)
         assert (got_t[~done] == ot[~done]).all() and not np.array_equal(got_t[done], to_np(r.obs)[done])  # finished rows differ from the fresh game
 
 
+@pytest.mark.parametrize("mode", [abi.SLIDE_ICE, abi.SLIDE_TEMPER])
+def test_obs_terminal_trail_with_slide_tiles(mode):
+    """a game that ends on a slide tick leaves an uncommitted body AND slide tile per player: both belong to its terminal frame"""
+    N, W = 2000, 12
+    g, o = make_pair(N, W, W, layout="trail", obs_dtype=abi.BF16, obs_enc=abi.ENC_POPUP3, seed=31, slide_mode=mode, slide_rate=0.6)
+    g.reset(); o.reset()
+    shape = (N, 2, 3, W + 2, W + 2)
+    for t in range(12):
+        gt = torch.full(shape, 7, dtype=torch.bfloat16, device="cuda")
+        ot = to_np(torch.full(shape, 7, dtype=torch.bfloat16)).copy()
+        r = g.env.step(obs_terminal=gt)
+        assert_same_step(tuple(to_np(x) for x in r), o.step(obs_terminal=ot), "tick %d" % t)
+        assert np.array_equal(to_np(gt), ot), t
+
+
 def test_obs_terminal_is_refused_where_unsupported():
     from tron_b200 import _lib
     from tron_b200.batch_env import BatchedTron
-    env = BatchedTron(64, 20, 20, layout="trail", obs_dtype=torch.int8)
+    # the trail layout renders terminal frames with its bulk-store kernel, which needs observation rows of a multiple of 16 bytes
+    env = BatchedTron(64, 19, 19, layout="trail", obs_dtype=torch.int8)  # 2 * 441 bytes per game
     env.reset()
     with pytest.raises(_lib.TronError):
         env.step(obs_terminal=env.new_obs())

@@ -74,7 +74,10 @@ def one_case(rng, case):
     assert (a is None and b is None) or np.array_equal(a, b), desc
     if slide == abi.SLIDE_TEMPER:
         assert np.array_equal(g.env.slide_params.cpu().numpy(), o.slide_params), desc + " temper draws"
-    want_terminal = enc != abi.ENC_NONE and layout != "trail" and rng.random() < 0.3
+    C = (W + 2) * (H + 2)
+    row = 2 * abi.enc_planes(enc) * C * abi.dtype_size(dt)
+    terminal_ok = layout != "trail" or (C % 4 == 0 and row % 16 == 0 and row <= 200 * 1024)  # trail: bulk-store kernel only
+    want_terminal = enc != abi.ENC_NONE and terminal_ok and rng.random() < 0.3
     use_tape = rng.random() < 0.5
     for t in range(int(rng.integers(5, 40))):
         act = rng.integers(0, 4, size=(N, 2)).astype(rng.choice([np.uint8, np.int32, np.int64])) if use_tape else None

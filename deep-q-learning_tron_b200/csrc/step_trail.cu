@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
 // the row, and restores the patched cells.  All global observation bytes are written by the bulk engine exactly once -- there
 // are no scattered element stores to HBM and no write-ordering between the two proxies to reason about.
 template <int OD, int LP, bool CP, int MODE>
-__global__ void __launch_bounds__(kTrailThreads) step_trail_obs_bulk_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(const StepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
     constexpr int NP = LP + (CP ? 1 : 0);
@@ -455,9 +455,11 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_bulk_kernel(cons
         const long long si = p.state_off + senv;
         const int nmax = max(n1, n2);
         auto cell_of = [&](unsigned u) { return ((int)(u & 0x7F) + 1) * Hc + (int)(u >> 8) + 1; };
+        // L2 reads: another lane of this warp may have appended the entry in this tick; the first word per lane is kept for the restore pass
+        const uint32_t v_first = lane < nmax ? __ldcg(st.word(si, lane)) : 0u;
         auto lists = [&](bool restore) {
             for (int k = lane; k < nmax; k += 32) {
-                const uint32_t v = __ldcg(st.word(si, k));  // L2 read: another lane of this warp may have appended the entry in this tick
+                const uint32_t v = k == lane ? v_first : __ldcg(st.word(si, k));
 #pragma unroll
                 for (int pl2 = 0; pl2 < 2; ++pl2) {
                     if (k >= (pl2 ? n2 : n1)) continue;
@@ -486,8 +488,9 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_bulk_kernel(cons
         if (lane == 0) { patch(hcell1, TRON_TILE_P1_HEAD); patch(hcell2, TRON_TILE_P2_HEAD); }
         fence_proxy_async();  // every lane: its generic-proxy writes to the row become visible to the bulk engine
         __syncwarp();
-        // -- the row leaves as bulk stores, 2 KB per lane and round
-        for (uint32_t o = (uint32_t)lane * 2048u; o < row; o += 32u * 2048u) bulk_s2g(dst + o, my + o, min(2048u, row - o));
+        // -- the row leaves as bulk stores, one chunk per lane and round
+        const uint32_t chunk = row >= 16384u ? 8192u : 2048u;  // bytes per lane and bulk store (profiles/r2_trail_obs_tune.jsonl)
+        for (uint32_t o = (uint32_t)lane * chunk; o < row; o += 32u * chunk) bulk_s2g(dst + o, my + o, min(chunk, row - o));
         bulk_commit();
         bulk_wait_read_all();
         __syncwarp();
@@ -554,7 +557,8 @@ static int launch_trail_obs_one(StepParams p, cudaStream_t s) {
         const size_t smem = (size_t)nwarp * row;
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
         // games per warp: about three waves of CTAs (the template row is built once per CTA, so few, long-lived CTAs), at most one game per lane
-        int gpw = (int)((long long)p.N / (3LL * ctas_per_sm * sm_count() * nwarp));
+        // (more waves for long rows, where the tail of the last wave is what costs; fewer for short rows, where the template build does)
+        int gpw = (int)((long long)p.N / ((row >= 8192 ? 8LL : 3LL) * ctas_per_sm * sm_count() * nwarp));
         gpw = gpw < 1 ? 1 : (gpw > 32 ? 32 : gpw);
         p.G = nwarp * gpw;
         const unsigned grid = (unsigned)(((long long)p.N + p.G - 1) / p.G);

@@ -117,6 +117,20 @@ def dtype_size(dt):
     return {U8: 1, I8: 1, BF16: 2, I32: 4, F32: 4, I64: 8}[dt]
 
 
+def trail_bulk_ok(width, height, enc, dtype):
+    """does the trail layout's bulk-store observation kernel (template rows in shared memory, step_trail.cu) cover this
+    configuration?  It renders terminal frames; the element-store kernel it falls back to does not."""
+    row = 2 * enc_planes(enc) * cells_per_env(width, height) * dtype_size(dtype)
+    if row == 0:
+        return False
+    grp = 1
+    while (grp * row) % 16:
+        grp *= 2
+    while grp < 16 and grp * row < 8192:
+        grp *= 2
+    return ((grp * row + 15) & ~15) <= 200 * 1024
+
+
 def state_bytes(n_envs, width, height, layout=LAYOUT_TILE8):
     per = 32 if layout == LAYOUT_BITS10 else 48 if layout == LAYOUT_BITS else cells_per_env(width, height)
     if layout == LAYOUT_TRAIL:  # 64 hot bytes (header + 12 list words) + the cold tail of the lists + the bitmap of the cells it names

@@ -31,11 +31,10 @@ def auto_layout(width, height, obs_enc, slide_mode, obs_dtype=torch.bfloat16):
     if enc_none:
         return "trail" if cells >= 1024 else "tile8"
     # fused observations on boards from 20x20 up: the trail lists with bulk-stored template rows beat the int8 grid (no grid
-    # traffic at all; profiles/r2_large_obs.jsonl) wherever that kernel applies (observation rows of a multiple of 16 bytes)
+    # traffic at all; profiles/r2_trail_obs.jsonl) wherever that kernel applies
     enc = _ENC_OF[obs_enc] if isinstance(obs_enc, str) else int(obs_enc)
-    es = abi.dtype_size(_CODE_OF[obs_dtype] if isinstance(obs_dtype, torch.dtype) else int(obs_dtype))
-    row = 2 * abi.enc_planes(enc) * cells * es
-    if width * height >= 400 and width <= 126 and height <= 126 and cells % 4 == 0 and row % 16 == 0 and row <= 200 * 1024:
+    dt = _CODE_OF[obs_dtype] if isinstance(obs_dtype, torch.dtype) else int(obs_dtype)
+    if width * height >= 400 and width <= 126 and height <= 126 and abi.trail_bulk_ok(width, height, enc, dt):
         return "trail"
     return "tile8"
 _SLIDE_OF = {None: abi.SLIDE_NONE, "tape": abi.SLIDE_TAPE, "ice": abi.SLIDE_ICE, "temper": abi.SLIDE_TEMPER}

@@ -376,25 +376,31 @@ __global__ void __launch_bounds__(kTrailThreads) step_trail_obs_kernel(const Ste
     }
 }
 
-// ---- fused tick + observation planes, BULK-STORE edition (the default whenever a game's observation row is a multiple of 16 B) ----
+static inline bool mode_is_multi(const StepParams& p) { return p.obs_every_tick && p.T > 1; }
+
+// ---- fused tick + observation planes, BULK-STORE edition (the default) -----------------------------------------------------
 // A game's observation row [2,P,C] equals the encoded TEMPLATE row (border WALL, interior EMPTY) except at its trail cells and
-// its two heads.  Each warp keeps one encoded template row in shared memory.  Per game it patches those few cells IN SHARED
-// MEMORY, hands the whole row to the TMA engine (cp.async.bulk shared -> global: a handful of instructions per game instead of
-// one store instruction per 16 bytes per lane, and the DRAM sees row-sized contiguous bursts), waits until the engine has READ
-// the row, and restores the patched cells.  All global observation bytes are written by the bulk engine exactly once -- there
-// are no scattered element stores to HBM and no write-ordering between the two proxies to reason about.
+// its two heads.  Each warp keeps `grp` copies of the encoded template row back to back in shared memory (a "group buffer").
+// Per group of grp consecutive games it patches those few cells IN SHARED MEMORY, hands the whole buffer to the TMA engine
+// (cp.async.bulk shared -> global: a handful of instructions per group instead of one store instruction per 16 bytes per lane,
+// and the DRAM sees long contiguous bursts), waits until the engine has READ the buffer, and restores the patched cells.
+// grp is a power of two such that (a) grp * row is a multiple of 16 bytes -- game e always uses sub-row e % grp, so shared and
+// global addresses are congruent mod 16 and ANY run of sub-rows can leave as one bulk store of its 16-byte-aligned interior plus
+// at most 15 bytes of byte stores at either end (partial groups at the end of a batch, single terminal frames) -- and (b) short
+// rows are batched to ~8 KB per store.  Apart from those end fragments every observation byte is written by the bulk engine,
+// exactly once: no scattered element stores to HBM, no write ordering between the two proxies to reason about.
 template <int OD, int LP, bool CP, int MODE>
-__global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(const StepParams p) {
+__global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(const StepParams p, const int grp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ES = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
     constexpr int NP = LP + (CP ? 1 : 0);
     const int C = p.C, G = p.G, Hc = p.Hc, tid = threadIdx.x, lane = tid & 31, P = p.P, warp = tid >> 5, nwarp = (int)blockDim.x >> 5;
-    const uint32_t row = 2u * (uint32_t)P * (uint32_t)C * ES;  // bytes of one game's observations; the launcher guarantees row % 16 == 0, C % 4 == 0
-    char* my = (char*)smem_raw + (size_t)warp * row;            // this warp's row buffer
-    // 1. the encoded template row: built once per CTA in warp 0's buffer, copied to the other warps' buffers
-    {
-        const int per = C / 4;
-        for (int ch = tid; ch < per; ch += (int)blockDim.x) {
+    const uint32_t row = 2u * (uint32_t)P * (uint32_t)C * ES;        // bytes of one game's observations
+    const uint32_t wbytes = ((uint32_t)grp * row + 15u) & ~15u;      // one warp's group buffer
+    char* my = (char*)smem_raw + (size_t)warp * wbytes;
+    // 1. the encoded template row: built once per CTA (sub-row 0 of warp 0), then replicated into every sub-row of every warp
+    if ((C & 3) == 0) {
+        for (int ch = tid; ch < C / 4; ch += (int)blockDim.x) {
             const int c0 = ch * 4;
             uint32_t cells = 0;
 #pragma unroll
@@ -410,21 +416,40 @@ __global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(c
                 for (int q = 0; q < NP; ++q) {
                     uint32_t o[Enc4<OD>::WORDS];
                     if (q < LP) Enc4<OD>::run(p.tab[pl][q < LP ? q : 0], sel, o); else Enc4<OD>::fill(p.const_plane, o);
-                    uint32_t* dst = (uint32_t*)((char*)smem_raw + ((size_t)(pl * P + q) * C + (size_t)c0) * ES);
+                    uint32_t* dst = (uint32_t*)((char*)smem_raw + ((size_t)(pl * P + q) * C + (size_t)c0) * ES);  // C % 4 == 0: 4-byte aligned
 #pragma unroll
                     for (int w = 0; w < Enc4<OD>::WORDS; ++w) dst[w] = o[w];
                 }
         }
-        fence_proxy_async();  // warp 0's buffer is written by every thread of the CTA: each writer orders its writes before the bulk engine's reads
-        __syncthreads();
-        if (warp > 0)
-            for (uint32_t o = (uint32_t)lane * 16u; o < row; o += 512u) *(uint4*)(my + o) = *(const uint4*)((const char*)smem_raw + o);
-        fence_proxy_async();
-        __syncthreads();  // warp 0 must not patch its buffer while the others still copy from it
+    } else {
+        for (int c = tid; c < C; c += (int)blockDim.x) {
+            const int r = c / Hc, q0 = c - r * Hc;
+            const int tile = (r == 0 || r == p.W + 1 || q0 == 0 || q0 == p.H + 1) ? TRON_TILE_WALL : TRON_TILE_EMPTY;
+            for (int pl = 0; pl < 2; ++pl)
+                for (int q = 0; q < NP; ++q) {
+                    char* plane = (char*)smem_raw + (size_t)(pl * P + q) * C * ES;
+                    if (q < LP) store_elem<OD>(plane, c, p.tab[pl][q < LP ? q : 0], tile);
+                    else {
+                        uint32_t o[Enc4<OD>::WORDS];
+                        Enc4<OD>::fill(p.const_plane, o);
+                        if (ES == 4) ((uint32_t*)plane)[c] = o[0]; else if (ES == 2) ((unsigned short*)plane)[c] = (unsigned short)o[0]; else ((unsigned char*)plane)[c] = (unsigned char)o[0];
+                    }
+                }
+        }
     }
+    __syncthreads();
+    for (int j = 0; j < grp; ++j) {
+        if (warp == 0 && j == 0) continue;
+        char* dst = my + (size_t)j * row;
+        if ((row & 3u) == 0) for (uint32_t o = (uint32_t)lane * 4u; o < row; o += 128u) *(uint32_t*)(dst + o) = *(const uint32_t*)((const char*)smem_raw + o);
+        else for (uint32_t o = (uint32_t)lane; o < row; o += 32u) dst[o] = ((const char*)smem_raw)[o];
+    }
+    fence_proxy_async();  // every writer orders its generic-proxy writes before the bulk engine's reads
+    __syncthreads();      // warp 0 must not patch its buffer while the others still copy from it
+
     const long long env0 = (long long)blockIdx.x * G;
     const int nG = (int)min((long long)G, (long long)p.N - env0);
-    const int gpw = G / nwarp;
+    const int gpw = G / nwarp;  // a multiple of grp (launcher)
     const int local = warp * gpw + lane;
     const bool owner = lane < gpw && local < nG;
     const long long env = env0 + local;
@@ -442,24 +467,40 @@ __global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(c
         if (MODE == MODE_STEP) g.load_hot(st, gi, kTrailHot);
         if (MODE == MODE_OBSERVE) emit_extra(p, env);
     }
-    // value of `tile` on plane (pl, q) written into this warp's row buffer at `cell`
-    auto patch = [&](int cell, int tile) {
+    // the 32 lanes are split evenly over the grp sub-rows: lane -> (sub-row j, position `sub` among the lpg lanes of that sub-row)
+    const int lpg = 32 / grp, j = lane / lpg, sub = lane - j * lpg;
+    char* mine = my + (size_t)j * row;
+    auto patch = [&](int cell, int tile) {  // value of `tile` on every lut plane of this lane's sub-row
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl)
 #pragma unroll
-            for (int q = 0; q < LP; ++q) store_elem<OD>(my + (size_t)(pl * P + q) * C * ES, cell, p.tab[pl][q], tile);
+            for (int q = 0; q < LP; ++q) store_elem<OD>(mine + (size_t)(pl * P + q) * C * ES, cell, p.tab[pl][q], tile);
     };
-    // render one game of this warp: patch the row buffer with the list entries in memory (n1 / n2 per player), the entries of the
-    // current tick that exist only in registers (fb bodies, fs slide tiles; 0xFFFF = none) and the heads; bulk-store it; restore it
-    auto render = [&](long long senv, int n1, int n2, uint32_t fb, uint32_t fs, int hr1, int hc1, int hr2, int hc2, char* dst) {
-        const long long si = p.state_off + senv;
-        const int nmax = max(n1, n2);
-        auto cell_of = [&](unsigned u) { return ((int)(u & 0x7F) + 1) * Hc + (int)(u >> 8) + 1; };
+    auto cell_of = [&](unsigned u) { return ((int)(u & 0x7F) + 1) * Hc + (int)(u >> 8) + 1; };
+    // bytes [lo, hi) of this warp's buffer -> the same offsets behind gdst (gdst and the buffer are both 16-byte aligned)
+    auto store_range = [&](uint32_t lo, uint32_t hi, char* gdst) {
+        const uint32_t alo = (lo + 15u) & ~15u, ahi = hi & ~15u;
+        if (alo < ahi) {
+            const uint32_t chunk = (ahi - alo) >= 16384u ? 8192u : 2048u;  // bytes per lane and bulk store (profiles/r2_trail_obs_tune.jsonl)
+            for (uint32_t o = alo + (uint32_t)lane * chunk; o < ahi; o += 32u * chunk) bulk_s2g(gdst + o, my + o, min(chunk, ahi - o));
+            if ((uint32_t)lane < alo - lo) gdst[lo + lane] = my[lo + lane];
+            if ((uint32_t)lane < hi - ahi) gdst[ahi + lane] = my[ahi + lane];
+        } else {
+            for (uint32_t o = lo + (uint32_t)lane; o < hi; o += 32u) gdst[o] = my[o];
+        }
+    };
+    // One group: the games owned by lanes s0 .. s0+grp-1 of this warp; bit jj of `act` = render sub-row jj.  The per-lane arguments
+    // describe the game of THIS lane's sub-row: list lengths in memory (n1 / n2), the entries of the current tick that exist only in
+    // registers (fb bodies, fs slide tiles; 0xFFFF = none), the heads.  Patch, bulk-store the flagged sub-rows, wait, restore.
+    auto render_group = [&](unsigned act, int s0, int n1, int n2, uint32_t fb, uint32_t fs, int hr1, int hc1, int hr2, int hc2, char* gdst) {
+        const bool on = (act >> j) & 1u;
+        const long long si = p.state_off + env0 + warp * gpw + s0 + j;
+        const int nmax = on ? max(n1, n2) : 0;
         // L2 reads: another lane of this warp may have appended the entry in this tick; the first word per lane is kept for the restore pass
-        const uint32_t v_first = lane < nmax ? __ldcg(st.word(si, lane)) : 0u;
+        const uint32_t v_first = sub < nmax ? __ldcg(st.word(si, sub)) : 0u;
         auto lists = [&](bool restore) {
-            for (int k = lane; k < nmax; k += 32) {
-                const uint32_t v = k == lane ? v_first : __ldcg(st.word(si, k));
+            for (int k = sub; k < nmax; k += lpg) {
+                const uint32_t v = k == sub ? v_first : __ldcg(st.word(si, k));
 #pragma unroll
                 for (int pl2 = 0; pl2 < 2; ++pl2) {
                     if (k >= (pl2 ? n2 : n1)) continue;
@@ -470,38 +511,44 @@ __global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(c
                                         : pl2 ? ((u & 0x80) ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY) : ((u & 0x80) ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY));
                 }
             }
-            if (lane < 4) {  // the tick's own entries (terminal frames: the finished game's last bodies / slide tiles were never committed)
-                const uint32_t w = (lane & 1) ? fs : fb;
-                const unsigned u = (lane & 2) ? (w >> 16) : (w & 0xFFFFu);
-                if (u != 0xFFFFu) {
+            if (on)
+                for (int q = sub; q < 4; q += lpg) {  // the tick's own entries (terminal frames: the finished game's last bodies / slide tiles were never committed)
+                    const uint32_t w = (q & 1) ? fs : fb;
+                    const unsigned u = (q & 2) ? (w >> 16) : (w & 0xFFFFu);
+                    if (u == 0xFFFFu) continue;
                     const int cell = cell_of(u & 0xFF7Fu);
-                    if (TRON_DCHECK(cell >= 0 && cell < C, DBG_CELL_INDEX))
-                        patch(cell, restore ? (int)TRON_TILE_EMPTY
-                                            : (lane & 2) ? ((lane & 1) ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY) : ((lane & 1) ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY));
+                    if (!TRON_DCHECK(cell >= 0 && cell < C, DBG_CELL_INDEX)) continue;
+                    patch(cell, restore ? (int)TRON_TILE_EMPTY
+                                        : (q & 2) ? ((q & 1) ? TRON_TILE_P2_SLIDE : TRON_TILE_P2_BODY) : ((q & 1) ? TRON_TILE_P1_SLIDE : TRON_TILE_P1_BODY));
                 }
-            }
         };
         // -- patch: trail cells of both players (distinct cells), then the heads (P2 last, it wins a shared cell)
         lists(false);
         __syncwarp();
         const int hcell1 = (hr1 + 1) * Hc + hc1 + 1, hcell2 = (hr2 + 1) * Hc + hc2 + 1;
-        if (lane == 0) { patch(hcell1, TRON_TILE_P1_HEAD); patch(hcell2, TRON_TILE_P2_HEAD); }
-        fence_proxy_async();  // every lane: its generic-proxy writes to the row become visible to the bulk engine
+        if (on && sub == 0) { patch(hcell1, TRON_TILE_P1_HEAD); patch(hcell2, TRON_TILE_P2_HEAD); }
+        fence_proxy_async();  // every lane: its generic-proxy writes to the buffer become visible to the bulk engine
         __syncwarp();
-        // -- the row leaves as bulk stores, one chunk per lane and round
-        const uint32_t chunk = row >= 16384u ? 8192u : 2048u;  // bytes per lane and bulk store (profiles/r2_trail_obs_tune.jsonl)
-        for (uint32_t o = (uint32_t)lane * chunk; o < row; o += 32u * chunk) bulk_s2g(dst + o, my + o, min(chunk, row - o));
+        // -- every maximal run of flagged sub-rows leaves as one range
+        for (unsigned m = act; m;) {
+            const int a = __ffs(m) - 1;
+            int b = a;
+            while ((m >> b) & 1u) ++b;
+            store_range((uint32_t)a * row, (uint32_t)b * row, gdst);
+            m &= ~((1u << b) - 1u);
+        }
         bulk_commit();
         bulk_wait_read_all();
         __syncwarp();
         // -- restore the template at the patched cells (trail cells are interior cells; a crashed head may sit on the border)
         lists(true);
-        if (lane == 0) {
+        if (on && sub == 0) {
             patch(hcell1, (hr1 < 0 || hc1 < 0 || hr1 >= p.W || hc1 >= p.H) ? TRON_TILE_WALL : TRON_TILE_EMPTY);
             patch(hcell2, (hr2 < 0 || hc2 < 0 || hr2 >= p.W || hc2 >= p.H) ? TRON_TILE_WALL : TRON_TILE_EMPTY);
         }
         __syncwarp();
     };
+    const unsigned FULL = 0xFFFFFFFFu;
     const int T = MODE == MODE_STEP ? p.T : 1;
     for (int t = 0; t < T; ++t) {
         bool fin = false;
@@ -516,14 +563,14 @@ __global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(c
         if (MODE == MODE_STEP && p.obs_term) {
             // terminal frames (tron_step_args.obs_terminal; single-tick calls only): the last frame of the games that finished in this
             // tick and were auto-reset -- their lists as they still stand in memory, this tick's uncommitted entries, the final heads
-            unsigned m = __ballot_sync(0xFFFFFFFFu, fin);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                render(env0 + warp * gpw + src, __shfl_sync(0xFFFFFFFFu, on0, src), __shfl_sync(0xFFFFFFFFu, on1, src),
-                       __shfl_sync(0xFFFFFFFFu, ofb, src), __shfl_sync(0xFFFFFFFFu, ofs, src),
-                       __shfl_sync(0xFFFFFFFFu, e.tr1, src), __shfl_sync(0xFFFFFFFFu, e.tc1, src), __shfl_sync(0xFFFFFFFFu, e.tr2, src), __shfl_sync(0xFFFFFFFFu, e.tc2, src),
-                       (char*)p.obs_term + (size_t)(env0 + warp * gpw + src) * row);
+            const unsigned mfin = __ballot_sync(FULL, fin);
+            for (int s0 = 0; s0 < gpw; s0 += grp) {
+                const unsigned act = (mfin >> s0) & ((1u << grp) - 1u);
+                if (!act) continue;
+                const int sl = s0 + j;
+                render_group(act, s0, __shfl_sync(FULL, on0, sl), __shfl_sync(FULL, on1, sl), __shfl_sync(FULL, ofb, sl), __shfl_sync(FULL, ofs, sl),
+                             __shfl_sync(FULL, e.tr1, sl), __shfl_sync(FULL, e.tc1, sl), __shfl_sync(FULL, e.tr2, sl), __shfl_sync(FULL, e.tc2, sl),
+                             (char*)p.obs_term + (size_t)(env0 + warp * gpw + s0) * row);
             }
         }
         if (!(MODE == MODE_OBSERVE || p.obs_every_tick || t == T - 1)) continue;
@@ -531,12 +578,14 @@ __global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(c
         const size_t tick_off = (MODE == MODE_STEP && p.obs_every_tick) ? (size_t)t * (size_t)p.N * row : 0;
         char* obase = (char*)p.obs + tick_off;
         __syncwarp();  // the entries appended in this tick (plain global stores of the owning lanes) are read by the whole warp below
-        for (int src = 0; src < gpw; ++src) {  // warp-uniform loop over this warp's games
-            if (warp * gpw + src >= nG) break;
-            const long long senv = env0 + warp * gpw + src;
-            render(senv, __shfl_sync(0xFFFFFFFFu, g.n0, src), __shfl_sync(0xFFFFFFFFu, g.n1, src), 0xFFFFFFFFu, 0xFFFFFFFFu,
-                   __shfl_sync(0xFFFFFFFFu, e.r1, src), __shfl_sync(0xFFFFFFFFu, e.c1, src), __shfl_sync(0xFFFFFFFFu, e.r2, src), __shfl_sync(0xFFFFFFFFu, e.c2, src),
-                   obase + (size_t)senv * row);
+        for (int s0 = 0; s0 < gpw; s0 += grp) {  // warp-uniform loop over this warp's groups
+            const int first = warp * gpw + s0;
+            if (first >= nG) break;
+            const int ng = min(grp, nG - first);
+            const int sl = s0 + j;
+            render_group((1u << ng) - 1u, s0, __shfl_sync(FULL, g.n0, sl), __shfl_sync(FULL, g.n1, sl), 0xFFFFFFFFu, 0xFFFFFFFFu,
+                         __shfl_sync(FULL, e.r1, sl), __shfl_sync(FULL, e.c1, sl), __shfl_sync(FULL, e.r2, sl), __shfl_sync(FULL, e.c2, sl),
+                         obase + (size_t)(env0 + first) * row);
         }
     }
     if (MODE == MODE_STEP && owner) {
@@ -545,26 +594,34 @@ __global__ void __launch_bounds__(kTrailThreads, 6) step_trail_obs_bulk_kernel(c
     }
 }
 
-constexpr size_t kTrailBulkSmem = 200 * 1024;  // shared memory a CTA of the bulk-store kernel may use for its row buffers
+constexpr size_t kTrailBulkSmem = 200 * 1024;  // shared memory a CTA of the bulk-store kernel may use for its group buffers
 
 template <int OD, int LP, bool CP, int MODE>
 static int launch_trail_obs_one(StepParams p, cudaStream_t s) {
     const size_t es = OD == TRON_F32 ? 4 : OD == TRON_BF16 ? 2 : 1;
     const size_t row = 2 * (size_t)p.P * (size_t)p.C * es;
-    if (!(p.variant & 32) && row % 16 == 0 && p.C % 4 == 0 && ((uintptr_t)p.obs & 15u) == 0 && row <= kTrailBulkSmem) {
-        // bulk-store edition: one row buffer per warp; as many warps (<= 4) and CTAs per SM as the shared memory holds
-        const int nwarp = (int)std::min<size_t>(4, kTrailBulkSmem / row);
-        const size_t smem = (size_t)nwarp * row;
-        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(227 * 1024) / (smem + 1024)));
-        // games per warp: about three waves of CTAs (the template row is built once per CTA, so few, long-lived CTAs), at most one game per lane
-        // (more waves for long rows, where the tail of the last wave is what costs; fewer for short rows, where the template build does)
+    // games per group: the smallest power of two that makes a group a multiple of 16 bytes, doubled while a group stays below ~8 KB
+    int grp = 1;
+    while ((grp * row) % 16 != 0) grp *= 2;  // <= 16: row is even
+    while (grp < 16 && (size_t)grp * row < 8192) grp *= 2;
+    const size_t wbytes = ((size_t)grp * row + 15) & ~(size_t)15;
+    const bool ticks_aligned = !(mode_is_multi(p)) || ((size_t)p.N * row) % 16 == 0;  // every tick's block of p.obs must start 16-byte aligned
+    if (!(p.variant & 32) && ((uintptr_t)p.obs & 15u) == 0 && ((uintptr_t)p.obs_term & 15u) == 0 && wbytes <= kTrailBulkSmem && ticks_aligned) {
+        // as many warps (<= 4) and CTAs per SM as the shared memory holds
+        const int nwarp = (int)std::min<size_t>(4, kTrailBulkSmem / wbytes);
+        const size_t smem = (size_t)nwarp * wbytes;
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(6, (size_t)(227 * 1024) / (smem + 1024)));
+        // games per warp: a few waves of CTAs (the template is built once per CTA, so few, long-lived CTAs; more waves for long rows,
+        // where the tail of the last wave is what costs), whole groups, at most one game per lane
         int gpw = (int)((long long)p.N / ((row >= 8192 ? 8LL : 3LL) * ctas_per_sm * sm_count() * nwarp));
-        gpw = gpw < 1 ? 1 : (gpw > 32 ? 32 : gpw);
+        gpw = gpw > 32 ? 32 : gpw;
+        gpw = gpw / grp * grp;
+        gpw = gpw < grp ? grp : gpw;
         p.G = nwarp * gpw;
         const unsigned grid = (unsigned)(((long long)p.N + p.G - 1) / p.G);
         auto kernel = step_trail_obs_bulk_kernel<OD, LP, CP, MODE>;
         if (ensure_dynamic_smem((const void*)kernel, smem) != TRON_OK) return TRON_ERR_CUDA;
-        kernel<<<grid, 32 * nwarp, smem, s>>>(p);
+        kernel<<<grid, 32 * nwarp, smem, s>>>(p, grp);
         return cudaGetLastError() == cudaSuccess ? TRON_OK : TRON_ERR_CUDA;
     }
     if (p.obs_term) return TRON_ERR_UNSUPPORTED;  // terminal frames are rendered by the bulk-store kernel only

@@ -66,7 +66,8 @@ def test_extra_side_features_follow_the_observed_game(layout):
 # ------------------------------------------------------------------ terminal frames
 @pytest.mark.parametrize("layout,W,dt,enc", [("tile8", 10, abi.BF16, abi.ENC_LUT1), ("bits10", 10, abi.BF16, abi.ENC_POPUP3), ("bits", 10, abi.F32, abi.ENC_LUT1),
                                              ("bits", 7, abi.I8, abi.ENC_POPUP3_CONST), ("tile8", 20, abi.I8, abi.ENC_LUT1), ("tile8", 50, abi.BF16, abi.ENC_LUT1),
-                                             ("trail", 10, abi.BF16, abi.ENC_POPUP3), ("trail", 20, abi.F32, abi.ENC_LUT1), ("trail", 46, abi.I8, abi.ENC_POPUP3_CONST)])
+                                             ("trail", 10, abi.BF16, abi.ENC_POPUP3), ("trail", 20, abi.F32, abi.ENC_LUT1), ("trail", 46, abi.I8, abi.ENC_POPUP3_CONST),
+                                             ("trail", 19, abi.I8, abi.ENC_LUT1), ("trail", 7, abi.BF16, abi.ENC_LUT1), ("trail", 33, abi.I8, abi.ENC_POPUP3)])
 def test_obs_terminal_holds_the_last_frame_of_finished_games(layout, W, dt, enc):
     N = 1500 if W <= 20 else 200
     g, o = make_pair(N, W, W, layout=layout, obs_dtype=dt, obs_enc=enc, seed=13, const_plane=2.0)
@@ -104,8 +105,9 @@ def test_obs_terminal_trail_with_slide_tiles(mode):
 def test_obs_terminal_is_refused_where_unsupported():
     from tron_b200 import _lib
     from tron_b200.batch_env import BatchedTron
-    # the trail layout renders terminal frames with its bulk-store kernel, which needs observation rows of a multiple of 16 bytes
-    env = BatchedTron(64, 19, 19, layout="trail", obs_dtype=torch.int8)  # 2 * 441 bytes per game
+    # the trail layout renders terminal frames with its bulk-store kernel, which keeps whole observation rows in shared memory
+    assert not abi.trail_bulk_ok(126, 126, abi.ENC_POPUP3_CONST, abi.F32)
+    env = BatchedTron(4, 126, 126, layout="trail", obs_dtype=torch.float32, obs_enc="popup3_const")  # 512 KB per game
     env.reset()
     with pytest.raises(_lib.TronError):
         env.step(obs_terminal=env.new_obs())

@@ -74,9 +74,7 @@ def one_case(rng, case):
     assert (a is None and b is None) or np.array_equal(a, b), desc
     if slide == abi.SLIDE_TEMPER:
         assert np.array_equal(g.env.slide_params.cpu().numpy(), o.slide_params), desc + " temper draws"
-    C = (W + 2) * (H + 2)
-    row = 2 * abi.enc_planes(enc) * C * abi.dtype_size(dt)
-    terminal_ok = layout != "trail" or (C % 4 == 0 and row % 16 == 0 and row <= 200 * 1024)  # trail: bulk-store kernel only
+    terminal_ok = layout != "trail" or abi.trail_bulk_ok(W, H, enc, dt)  # trail: bulk-store kernel only
     want_terminal = enc != abi.ENC_NONE and terminal_ok and rng.random() < 0.3
     use_tape = rng.random() < 0.5
     for t in range(int(rng.integers(5, 40))):

@@ -30,11 +30,11 @@ def auto_layout(width, height, obs_enc, slide_mode, obs_dtype=torch.bfloat16):
     cells = (width + 2) * (height + 2)
     if enc_none:
         return "trail" if cells >= 1024 else "tile8"
-    # fused observations on boards from 20x20 up: the trail lists with bulk-stored template rows beat the int8 grid (no grid
-    # traffic at all; profiles/r2_trail_obs.jsonl) wherever that kernel applies
+    # fused observations on boards from 12x12 up: the trail lists with bulk-stored template rows beat the int8 grid (no grid
+    # traffic at all; profiles/r2_trail_obs.jsonl, r2_small_boards_trail.jsonl) wherever that kernel applies
     enc = _ENC_OF[obs_enc] if isinstance(obs_enc, str) else int(obs_enc)
     dt = _CODE_OF[obs_dtype] if isinstance(obs_dtype, torch.dtype) else int(obs_dtype)
-    if width * height >= 400 and width <= 126 and height <= 126 and abi.trail_bulk_ok(width, height, enc, dt):
+    if width * height >= 144 and width <= 126 and height <= 126 and abi.trail_bulk_ok(width, height, enc, dt):
         return "trail"
     return "tile8"
 _SLIDE_OF = {None: abi.SLIDE_NONE, "tape": abi.SLIDE_TAPE, "ice": abi.SLIDE_ICE, "temper": abi.SLIDE_TEMPER}

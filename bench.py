@@ -534,7 +534,55 @@ def run_ours(a):
                                         "bytes_per_env_step": b5, "traffic": tr5, "traffic_source": tr5_src, "kernel": "step_trail_kernel",
                                         "note": "latency / issue bound, not bandwidth bound: see DESIGN.md section 6 and profiles/r2_step_trail_64x64_2M.json"},
                            "clocks": smp.stop(tw0, tw1) if rank == 0 else None}
-        del env5, r5, d5, w5
+        del env5
+        # the same pure tick under the epsilon-greedy proxy policy: long episodes, the lists outgrow the 12 hot entries and
+        # "is this cell free?" goes through the occupancy bitmap in the cold area
+        st5 = []
+        for eps in (0.5, 0.1, 0.003):
+            env_e = BatchedTron(n5, 64, 64, device=dev, obs_enc="none", reward="ddqn", seed=3, env_id_base=rank * n5, layout="trail",
+                                policy="free_eps", policy_epsilon=eps)
+            env_e.reset()
+            for _ in range(300):  # episode lengths reach their stationary mix (mean 31 ticks at epsilon 0.003)
+                env_e.step(reward=r5, done=d5, winner=w5, want_ep_len=False)
+            torch.cuda.synchronize()
+            q0 = env_e.stats_dict()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2 * TPS):
+                env_e.step(reward=r5, done=d5, winner=w5, want_ep_len=False)
+            e1.record(); torch.cuda.synchronize()
+            q1 = env_e.stats_dict()
+            ms_e = max_over_ranks(e0.elapsed_time(e1))
+            st5.append({"epsilon": eps, "value": world * n5 * 2 * TPS / (ms_e * 1e-3), "unit": UNIT, "n_gpus": world,
+                        "reset_fraction": sum_over_ranks(float(q1["episodes"] - q0["episodes"])) / sum_over_ranks(float(q1["env_steps"] - q0["env_steps"])),
+                        "mean_episode_ticks": (q1["ep_ticks"] - q0["ep_ticks"]) / max(1, q1["episodes"] - q0["episodes"])})
+            del env_e
+        configs["cfg5"]["eps_greedy_streams"] = st5
+        del r5, d5, w5
+        torch.cuda.empty_cache()
+        # beyond BASELINE: the 64x64 board WITH fused bf16 observations (SURVEY 8d's last table row), trail lists + bulk-stored template rows
+        n6 = 1 << 17
+        env6 = BatchedTron(n6, 64, 64, device=dev, obs_dtype=torch.bfloat16, obs_enc="lut1", reward="ddqn", seed=0, env_id_base=rank * n6, layout="auto")
+        o6 = env6.reset()
+        r6 = torch.empty((n6, 2), dtype=torch.float32, device=dev); d6 = torch.empty(n6, dtype=torch.uint8, device=dev); w6 = torch.empty(n6, dtype=torch.uint8, device=dev)
+        for _ in range(10):
+            env6.step(obs=o6, reward=r6, done=d6, winner=w6, want_ep_len=False)
+        torch.cuda.synchronize(); barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(TPS):
+            env6.step(obs=o6, reward=r6, done=d6, winner=w6, want_ep_len=False)
+        e1.record(); torch.cuda.synchronize()
+        ms6 = max_over_ranks(e0.elapsed_time(e1))
+        v6 = world * n6 * TPS / (ms6 * 1e-3)
+        b6 = 64 + 32 + 2 * 66 * 66 * 2 + 10  # hot state read, header + one list uint4 written, both observation planes, reward / done / winner
+        tr6, tr6_src = traffic_of("trail_bf16_lut1_64_%d" % n6)
+        configs["large_grid_fused_obs"] = {"workload": "64x64 grid, %d envs/GPU, fused bf16 1-plane observations, on-device Philox policy, state layout %s" % (n6, env6.layout),
+                                           "value": v6, "unit": UNIT, "n_gpus": world, "ticks": TPS, "ms_per_tick": ms6 / TPS,
+                                           "roofline": {"bound": "hbm", "achieved": v6 / world * b6 / 1e9, "peak": peak, "unit": "GB/s", "frac": v6 / world * b6 / 1e9 / peak,
+                                                        "bytes_per_env_step": b6, "traffic": tr6, "traffic_source": tr6_src, "kernel": "step_trail_obs_bulk_kernel"}}
+        del env6, o6, r6, d6, w6
         torch.cuda.empty_cache()
 
         from tron_b200 import dropin

@@ -86,8 +86,11 @@ enum {
     TRON_LAYOUT_TRAIL = 2, /* any grid, all modes: per game a 16-byte header + the list of trail cells both players left behind
                               (capacity W*H each, 2 bytes per cell).  The header and the first 12 list entries of every game (64
                               bytes, "hot") are stored as four dense uint4 arrays [4][N] so that a tick streams them fully
-                              coalesced; the rest of each list lives in a per-game cold area touched only by long episodes.
-                              Observations are rendered without materialising a grid.  Made for large grids. */
+                              coalesced; the rest of each list lives in a per-game cold area touched only by long episodes,
+                              next to an occupancy bitmap of the cells those cold entries name (one probe per lookup).
+                              Observations are rendered without materialising a grid: template rows in shared memory, patched
+                              and bulk-stored by the TMA engine.  The fastest layout for fused observations from 12x12 up and
+                              for pure ticks on large grids. */
     TRON_LAYOUT_BITS = 3   /* grids with W*H <= 128, all modes (incl. ice/temper): three 128-bit planes over the interior cells
                               (trail occupancy, trail owner, slide tile), stored as three dense uint4 arrays [3][N] = 48 bytes per
                               game; walls implicit, heads in the meta.  The bit-plane path for config.py's GAME_MODE="temper". */

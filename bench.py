@@ -534,6 +534,17 @@ def run_ours(a):
                                         "bytes_per_env_step": b5, "traffic": tr5, "traffic_source": tr5_src, "kernel": "step_trail_kernel",
                                         "note": "latency / issue bound, not bandwidth bound: see DESIGN.md section 6 and profiles/r2_step_trail_64x64_2M.json"},
                            "clocks": smp.stop(tw0, tw1) if rank == 0 else None}
+        # the same games advanced 16 ticks per launch (tron_step_many: state stays in registers between ticks, outputs [T,N] per tick)
+        for _ in range(2):
+            env5.step_many(16)
+        torch.cuda.synchronize(); barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(TPS // 4):
+            env5.step_many(16)
+        e1.record(); torch.cuda.synchronize()
+        ms5m = max_over_ranks(e0.elapsed_time(e1))
+        configs["cfg5"]["step_many_16_ticks_per_launch"] = {"value": world * n5 * 16 * (TPS // 4) / (ms5m * 1e-3), "unit": UNIT, "n_gpus": world}
         del env5
         # the same pure tick under the epsilon-greedy proxy policy: long episodes, the lists outgrow the 12 hot entries and
         # "is this cell free?" goes through the occupancy bitmap in the cold area

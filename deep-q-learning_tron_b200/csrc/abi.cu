@@ -137,7 +137,7 @@ int fill_params(const tron_step_args* a, int mode, StepParams& p) {
         p.r_win = a->reward_table.win; p.r_lose = a->reward_table.lose; p.r_draw = a->reward_table.draw;
     }
     if (mode != MODE_OBSERVE) p.spawn = a->spawn;
-    p.seed = a->seed; p.counter = a->counter; p.env_base = a->env_id_base; p.spawn_mode = a->spawn_mode;
+    p.seed = a->seed; philox_expand(a->seed, p.rk); p.counter = a->counter; p.env_base = a->env_id_base; p.spawn_mode = a->spawn_mode;
     p.counter_dev = (const unsigned long long*)a->counter_dev;
     return TRON_OK;
 }

@@ -45,6 +45,30 @@ static const int g_dbg_registered = dbg_register(dbg_read_unit);
 // ---------------------------------------------------------------------------------------------
 enum : uint32_t { TAG_ACTION = 1, TAG_SPAWN = 2, TAG_SLIDE = 3, TAG_EPS = 4, TAG_SAMPLE = 5, TAG_TEMPER = 6, TAG_FAIR = 7 };
 
+// The ten round keys of a seed (k0 + r * 0x9E3779B9, k1 + r * 0xBB67AE85) are the same for every game of a launch: the launcher
+// expands them once on the host into the kernel parameters (constant bank), which takes the two key additions per round off
+// every thread's instruction stream (the trail tick kernel is instruction-bound and calls Philox twice per game-tick).
+struct PhiloxKeys {
+    uint32_t k[20];
+};
+__host__ __device__ inline void philox_expand(unsigned long long seed, PhiloxKeys& rk) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        rk.k[2 * r] = k0; rk.k[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ uint4 philox(const PhiloxKeys& rk, unsigned long long counter, unsigned long long stream, uint32_t tag, uint32_t sub) {
+    uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = (uint32_t)stream;
+    uint32_t c3 = ((uint32_t)(stream >> 32) & 0xFFFFu) | ((tag & 0xFFu) << 16) | ((sub & 0xFFu) << 24);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ rk.k[2 * r]; c1 = l1; c2 = h0 ^ c3 ^ rk.k[2 * r + 1]; c3 = l0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
 __device__ __forceinline__ uint4 philox(unsigned long long seed, unsigned long long counter,
                                         unsigned long long stream, uint32_t tag, uint32_t sub) {
     uint32_t c0 = (uint32_t)counter, c1 = (uint32_t)(counter >> 32), c2 = (uint32_t)stream;
@@ -63,8 +87,8 @@ __device__ __forceinline__ uint4 philox(unsigned long long seed, unsigned long l
 // make_game spawn rule (reference tron/util.py:46-84).  Uniform: 4 draws over the grid.  Fair (mode="fair", util.py:48-62): a
 // random point, P1 uniform in the clipped 3x3 box around it, P2 uniform in the point-mirrored box.  Either way only
 // (x1,y1) is re-drawn while the two heads coincide (util.py:76-78).
-__device__ __forceinline__ char4 rng_spawn(unsigned long long seed, unsigned long long counter, unsigned long long env, int W, int H,
-                                           int fair) {
+template <class Key>  // Key: the 64-bit seed or its expanded PhiloxKeys
+__device__ __forceinline__ char4 rng_spawn(const Key& seed, unsigned long long counter, unsigned long long env, int W, int H, int fair) {
     int lo1x = 0, hi1x = W - 1, lo1y = 0, hi1y = H - 1, lo2x = 0, hi2x = W - 1, lo2y = 0, hi2y = H - 1;
     if (fair) {
         const uint4 q = philox(seed, counter, env, TAG_FAIR, 0);
@@ -85,7 +109,8 @@ __device__ __forceinline__ char4 rng_spawn(unsigned long long seed, unsigned lon
 }
 
 // Game.__init__ draws (reference tron/game.py:83,87): weight x2 in [40,101], degree in [-30,30].
-__device__ __forceinline__ char4 rng_temper(unsigned long long seed, unsigned long long counter, unsigned long long env) {
+template <class Key>
+__device__ __forceinline__ char4 rng_temper(const Key& seed, unsigned long long counter, unsigned long long env) {
     const uint4 r = philox(seed, counter, env, TAG_TEMPER, 0);
     return make_char4((signed char)(-30 + (int)__umulhi(r.z, 61u)), (signed char)(40 + (int)__umulhi(r.x, 62u)),
                       (signed char)(40 + (int)__umulhi(r.y, 62u)), 0);

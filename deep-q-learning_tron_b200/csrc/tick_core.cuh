@@ -28,6 +28,7 @@ struct StepParams {
     const uint8_t* env_mask;  // MODE_RESET
     unsigned long long* stats;
     unsigned long long seed, counter, env_base;
+    PhiloxKeys rk;  // round keys of `seed` (philox_expand, filled by whoever sets seed)
     const unsigned long long* counter_dev;
     long long ice_thr;
     long long eps_thr;  // TRON_POLICY_FREE_EPS: explore iff 24-bit mantissa <= eps_thr; < 0 -> uniform policy
@@ -162,7 +163,7 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
             a1 = read_action(p.actions, p.action_dtype, 2 * tn);
             a2 = read_action(p.actions, p.action_dtype, 2 * tn + 1);
         } else {
-            const uint4 r = philox(p.seed, ctr, genv, TAG_ACTION, 0);
+            const uint4 r = philox(p.rk, ctr, genv, TAG_ACTION, 0);
             a1 = (int)(r.x >> 30); a2 = (int)(r.y >> 30);
             if ((FEAT & FEAT_EPS) && p.eps_thr >= 0 && !(e.flags & TRON_FLAG_DONE)) {  // epsilon-greedy proxy: a random FREE neighbour unless exploring
 #pragma unroll
@@ -209,7 +210,7 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
             r1 += dr1; c1 += dc1;
             if ((FEAT & FEAT_SLIDE) && p.slide_mode != TRON_SLIDE_NONE) {  // reference game.py:163-178
                 uint4 sr = make_uint4(0, 0, 0, 0);
-                if (p.slide_mode >= TRON_SLIDE_ICE) sr = philox(p.seed, ctr, genv, TAG_SLIDE, 0);
+                if (p.slide_mode >= TRON_SLIDE_ICE) sr = philox(p.rk, ctr, genv, TAG_SLIDE, 0);
                 char4 tp = make_char4(0, 0, 0, 0);
                 if (p.slide_mode == TRON_SLIDE_TEMPER) tp = ((const char4*)p.slide_params)[env];
 #pragma unroll
@@ -304,14 +305,14 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
     char4 tp_now = make_char4(0, 0, 0, 0);
     bool tp_known = false;
     if (do_reset) {  // fresh game (reference game.py:70-91, util.py:70-78); the caller rebuilds the cells
-        const char4 sp = p.spawn ? ((const char4*)p.spawn)[tn] : rng_spawn(p.seed, ctr, genv, p.W, p.H, p.spawn_mode);
+        const char4 sp = p.spawn ? ((const char4*)p.spawn)[tn] : rng_spawn(p.rk, ctr, genv, p.W, p.H, p.spawn_mode);
         e.tr1 = e.r1; e.tc1 = e.c1; e.tr2 = e.r2; e.tc2 = e.c2;
         e.r1 = sp.x; e.c1 = sp.y; e.r2 = sp.z; e.c2 = sp.w;
         e.flags = TRON_FLAG_ALIVE1 | TRON_FLAG_ALIVE2 | (TRACK ? (e.flags & TRON_FLAG_BOXES_VALID) : 0u);
         e.k = 0;
         // Game.__init__ draws weight x2 and degree for every fresh game whatever the mode (reference game.py:83,87), tron_reset included
         if (p.slide_params) {
-            tp_now = rng_temper(p.seed, ctr, genv);
+            tp_now = rng_temper(p.rk, ctr, genv);
             tp_known = true;
             ((char4*)p.slide_params)[env] = tp_now;
         }

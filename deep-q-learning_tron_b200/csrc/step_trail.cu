@@ -125,15 +125,19 @@ struct TrailCells {
         dirty = 0xEu;
     }
 
-    __device__ __forceinline__ int get(int r, int c) const {
-        if (r < 0 || c < 0 || r >= W || c >= H) return TRON_TILE_WALL;
+    // the register part of get(): nonzero iff an entry of this tick or of list words 0..11 names the interior cell (r, c)
+    __device__ __forceinline__ uint32_t hot_hit(int r, int c) const {
         const uint32_t key = (uint32_t)(r & 0x7F) | ((uint32_t)c << 8), key2 = key | (key << 16);
         // per 16-bit half: (entry without its slide flag) ^ key is zero iff the entry is this cell; a running packed minimum
         // (VIMNMX3.U16x2, two list words per instruction) ends at zero iff any entry matched
         uint32_t acc = __vimin3_u16x2(0xFFFFFFFFu, (fb & 0xFF7FFF7Fu) ^ key2, (fs & 0xFF7FFF7Fu) ^ key2);
 #pragma unroll
         for (int w = 0; w < kTrailHot; w += 2) acc = __vimin3_u16x2(acc, (hot[w] & 0xFF7FFF7Fu) ^ key2, (hot[w + 1] & 0xFF7FFF7Fu) ^ key2);
-        uint32_t hit = zero_halves(acc);
+        return zero_halves(acc);
+    }
+    __device__ __forceinline__ int get(int r, int c) const {
+        if (r < 0 || c < 0 || r >= W || c >= H) return TRON_TILE_WALL;
+        uint32_t hit = hot_hit(r, c);
         if (max(n0, n1) > kTrailHot) {  // long episode: the cells of the list entries 12.. are in the bitmap
             const int w = r * wpr() + (c >> 5);
             if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) hit |= (bmp()[w] >> (c & 31)) & 1u;
@@ -204,6 +208,35 @@ struct TrailCells {
         dirty = 0;
     }
 };
+
+// The epsilon-greedy proxy policy probes the four neighbours of a head.  For a long game each probe needs one bitmap word from the
+// cold area: the four loads are issued together, before any of them is used (env_tick() calls this through ADL; one after the
+// other they were four dependent DRAM round trips per player and tick, and the kernel was bound by exactly that latency).
+__device__ __forceinline__ int free_neighbours(const TrailCells& g, const StepParams& p, const EnvState& e, int hr, int hc) {
+    const bool cold_on = max(g.n0, g.n1) > kTrailHot;
+    const uint32_t* b = g.bmp();
+    const int wpr = g.wpr();
+    int rr[4], cc[4];
+    bool inb[4];
+    uint32_t wv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        rr[k] = hr + (k == 2) - (k == 0); cc[k] = hc + (k == 1) - (k == 3);
+        inb[k] = rr[k] >= 0 && cc[k] >= 0 && rr[k] < g.W && cc[k] < g.H;
+        const int w = rr[k] * wpr + (cc[k] >> 5);
+        wv[k] = 0u;
+        if (cold_on && inb[k] && TRON_DCHECK(w < trail_bitmap_words(g.W, g.H), DBG_CELL_INDEX)) wv[k] = b[w];
+    }
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (!inb[k]) continue;
+        const uint32_t hit = g.hot_hit(rr[k], cc[k]) | ((wv[k] >> (cc[k] & 31)) & 1u);
+        const bool fr = !hit && !(rr[k] == e.r1 && cc[k] == e.c1) && !(rr[k] == e.r2 && cc[k] == e.c2);
+        m |= fr ? (1 << k) : 0;
+    }
+    return m;
+}
 
 // 64 registers (8 CTAs per SM): the kernel is issue-bound and the extra warps beat the 16 bytes of spill this costs (measured: an
 // 80-register build without spills is 7 % slower)

@@ -136,6 +136,21 @@ struct LoggedByteCells {
     }
 };
 
+// bit k set iff the neighbour of (hr, hc) in direction k is a free interior cell (no trail, no head) -- the epsilon-greedy proxy
+// policy's four probes.  Cell accessors with a memory-backed part overload this to issue their loads together (TrailCells).
+template <class Cells>
+__device__ __forceinline__ int free_neighbours(const Cells& g, const StepParams& p, const EnvState& e, int hr, int hc) {
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int rr = hr + (k == 2) - (k == 0), cc = hc + (k == 1) - (k == 3);
+        const bool fr = rr >= 0 && cc >= 0 && rr < p.W && cc < p.H && g.get(rr, cc) == TRON_TILE_EMPTY &&
+                        !(rr == e.r1 && cc == e.c1) && !(rr == e.r2 && cc == e.c2);
+        m |= fr ? (1 << k) : 0;
+    }
+    return m;
+}
+
 // One tick of the env whose cells start at `g`.  Updates `e` (fresh game state if it returns true = "rebuild this grid"),
 // writes reward/done/winner/ep_len for (tick t, env) and adds to the striped statistics.  TRACK maintains the dirty boxes.
 // pre_actions: the two actions already fetched (and range-folded by read_action) by a kernel that prefetches its inputs.
@@ -173,14 +188,8 @@ __device__ __forceinline__ bool env_tick(Cells& g, const StepParams& p, EnvState
                     act = (int)(w & 3u);
                     if ((long long)(w >> 8) <= p.eps_thr) continue;
                     const int hr = i ? e.r2 : e.r1, hc = i ? e.c2 : e.c1;
-                    int free_mask = 0, n_free = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int rr = hr + (k == 2) - (k == 0), cc = hc + (k == 1) - (k == 3);
-                        const bool fr = rr >= 0 && cc >= 0 && rr < p.W && cc < p.H && g.get(rr, cc) == TRON_TILE_EMPTY &&
-                                        !(rr == e.r1 && cc == e.c1) && !(rr == e.r2 && cc == e.c2);
-                        free_mask |= fr ? (1 << k) : 0; n_free += fr;
-                    }
+                    const int free_mask = free_neighbours(g, p, e, hr, hc);
+                    const int n_free = __popc((unsigned)free_mask);
                     if (n_free) {
                         int pick = (int)__umulhi(i ? r.w : r.z, (uint32_t)n_free);
 #pragma unroll

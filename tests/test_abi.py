@@ -73,6 +73,34 @@ def test_geometry_helpers_host_only(lib):
     assert lib.tron_abi_version() == abi.ABI_VERSION
 
 
+def test_state_bytes_of_every_layout_match_the_library(lib):
+    """the Python mirror of tron_state_bytes (used to size torch allocations) agrees with the C side for all four layouts"""
+    n = C.c_size_t()
+    for layout in (abi.LAYOUT_TILE8, abi.LAYOUT_BITS10, abi.LAYOUT_TRAIL, abi.LAYOUT_BITS):
+        for (w, h) in ((10, 10), (2, 2), (3, 4), (7, 9), (12, 12), (33, 20), (64, 64), (126, 126)):
+            if layout == abi.LAYOUT_BITS10 and (w, h) != (10, 10):
+                continue
+            if layout == abi.LAYOUT_BITS and w * h > 128:
+                continue
+            for n_envs in (1, 17, 4096):
+                assert lib.tron_state_bytes(n_envs, w, h, layout, C.byref(n)) == 0, (layout, w, h)
+                assert n.value == abi.state_bytes(n_envs, w, h, layout), (layout, w, h, n_envs)
+
+
+def test_auto_layout_choices():
+    """layout="auto": bit planes on config.py's board, trail lists for pure ticks on large grids and for fused observations from
+    12x12 up wherever the bulk-store kernel applies, the int8 grid otherwise"""
+    import torch
+    from tron_b200.batch_env import auto_layout
+    assert auto_layout(10, 10, "lut1", None) == "bits10" and auto_layout(10, 10, "popup3", "temper") == "bits"
+    assert auto_layout(64, 64, "none", None) == "trail" and auto_layout(8, 8, "none", None) == "tile8"
+    assert auto_layout(8, 8, "lut1", None) == "tile8" and auto_layout(11, 11, "lut1", None) == "tile8"
+    assert auto_layout(12, 12, "lut1", None) == "trail" and auto_layout(21, 21, "lut1", None, torch.int8) == "trail"
+    assert auto_layout(64, 64, "popup3", "ice", torch.float32) == "trail"
+    assert abi.trail_bulk_ok(126, 126, abi.ENC_LUT1, abi.BF16) and not abi.trail_bulk_ok(126, 126, abi.ENC_POPUP3_CONST, abi.F32)
+    assert auto_layout(126, 126, "popup3_const", None, torch.float32) == "tile8"  # rows too long for the shared-memory group buffer
+
+
 def test_plane_tables_match_oracle(lib):
     from oracle import c_oracle as oc
     for enc in (abi.ENC_LUT1, abi.ENC_POPUP3, abi.ENC_POPUP3_CONST):

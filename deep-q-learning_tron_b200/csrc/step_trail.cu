@@ -89,7 +89,10 @@ struct TrailCells {
         const int r = (int)(entry & 0x7Fu), c = (int)((entry >> 8) & 0xFFu);
         const int w = r * wpr() + (c >> 5);
         if (!TRON_DCHECK(r < W && c < H && w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) return;
-        atomicOr(bmp() + w, 1u << (c & 31));  // result unused -> RED.OR: no load the tick would have to wait for
+        // result unused -> RED.OR: no load the tick would have to wait for.  The reduction is performed in L2 and leaves a copy of the
+        // line in this SM's L1 stale, so every READ of the bitmap bypasses L1 (__ldcg): a later tick of the same launch (step_many)
+        // must see the bit (found by the differential fuzz: a missed collision let a list outgrow its capacity).
+        atomicOr(bmp() + w, 1u << (c & 31));
     }
     // the finished game's cold entries name the only bitmap words that can hold set bits: zero those (O(episode length), no extra state)
     __device__ __forceinline__ void unmark_all() {
@@ -140,7 +143,7 @@ struct TrailCells {
         uint32_t hit = hot_hit(r, c);
         if (max(n0, n1) > kTrailHot) {  // long episode: the cells of the list entries 12.. are in the bitmap
             const int w = r * wpr() + (c >> 5);
-            if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) hit |= (bmp()[w] >> (c & 31)) & 1u;
+            if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) hit |= (__ldcg(bmp() + w) >> (c & 31)) & 1u;  // L2 read, see mark()
         }
         return hit ? TRON_TILE_P1_BODY : TRON_TILE_EMPTY;  // callers only test for EMPTY
     }
@@ -225,7 +228,7 @@ __device__ __forceinline__ int free_neighbours(const TrailCells& g, const StepPa
         inb[k] = rr[k] >= 0 && cc[k] >= 0 && rr[k] < g.W && cc[k] < g.H;
         const int w = rr[k] * wpr + (cc[k] >> 5);
         wv[k] = 0u;
-        if (cold_on && inb[k] && TRON_DCHECK(w < trail_bitmap_words(g.W, g.H), DBG_CELL_INDEX)) wv[k] = b[w];
+        if (cold_on && inb[k] && TRON_DCHECK(w < trail_bitmap_words(g.W, g.H), DBG_CELL_INDEX)) wv[k] = __ldcg(b + w);  // L2 read, see mark()
     }
     int m = 0;
 #pragma unroll

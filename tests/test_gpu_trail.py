@@ -95,6 +95,22 @@ def test_trail_long_episodes_beyond_the_hot_window():
     assert longest >= 30
 
 
+@pytest.mark.parametrize("W,slide", [(8, abi.SLIDE_NONE), (8, abi.SLIDE_TEMPER), (20, abi.SLIDE_ICE)])
+def test_trail_step_many_sees_its_own_bitmap_updates(W, slide):
+    """several ticks per launch with long trails: the occupancy bit an earlier tick of the SAME launch set for a cold list entry
+    (a reduction performed in L2) must be seen by the later ticks' lookups, or a collision is missed and the lists run over"""
+    N = 20000
+    g, o = make_pair(N, W, W, seed=3, slide_mode=slide, slide_rate=0.15, policy=abi.POLICY_FREE_EPS, policy_epsilon=0.0, **KW)
+    g.reset(); o.reset()
+    longest = 0
+    for rnd in range(8):
+        r, want = g.step_many(7), o.step_many(7)
+        assert_same_step(r, want, "round %d" % rnd)
+        longest = max(longest, int(want[4].max()))
+    assert_same_state(g, o)
+    assert longest > 20  # trails well beyond the 12 entries kept in the hot words
+
+
 def test_trail_import_export_and_cross_layout():
     N, W = 700, 12
     a = GpuEnvNumpy(N, W, W, seed=5, **KW)

@@ -69,6 +69,8 @@ def one_case(rng, case):
               spawn_mode=int(rng.integers(0, 2)), policy=policy, policy_epsilon=float(rng.choice([0.0, 0.05, 0.5])),
               auto_reset=bool(rng.random() < 0.8), reward=str(rng.choice(["ddqn", "survivor", "acktr2"])))
     desc = "case %d: %s %dx%d N=%d enc=%d dt=%d slide=%d policy=%d auto=%s" % (case, layout, W, H, N, enc, dt, slide, policy, kw["auto_reset"])
+    if os.environ.get("FUZZ_VERBOSE"):
+        print(desc, flush=True)
     g, o = make_pair(N, W, H, **kw)
     a, b = g.reset(), o.reset()
     assert (a is None and b is None) or np.array_equal(a, b), desc

@@ -18,8 +18,8 @@
 // the tick: they give export / observation rendering the owner and slide flag of every cell) and an OCCUPANCY BITMAP over the
 // interior cells with one bit per cell that a cold entry names.  "Is this cell free?" for a long game is then the 12-word register
 // scan plus ONE 4-byte probe of the bitmap instead of a walk over the whole list (round 2 walked it: every probe of a long
-// game cost O(episode length) loads, the epsilon-greedy streams ran at a ninth of the short-episode rate); a reset zeroes only the
-// bitmap words that the finished game's cold entries name.  Unused entries of the hot words hold the impossible key 0xFFFF (see
+// game cost O(episode length) loads, the epsilon-greedy streams ran at a ninth of the short-episode rate); a reset of a game that had cold entries zeroes its
+// bitmap (512 B at 64x64, 16-byte stores).  Unused entries of the hot words hold the impossible key 0xFFFF (see
 // TrailCells), which makes "is this cell free?" a branch-free packed-minimum over the words (VIMNMX3.U16x2, 1.5 instructions per
 // list word); the kernel is instruction-issue-bound, not bandwidth-bound (profiles/r2_step_trail_64x64_2M.json: issue active 75 %,
 // DRAM 29 %), so instruction count is what the layout and these tricks buy.
@@ -88,23 +88,19 @@ struct TrailCells {
     __device__ __forceinline__ void mark(uint32_t entry) {
         const int r = (int)(entry & 0x7Fu), c = (int)((entry >> 8) & 0xFFu);
         const int w = r * wpr() + (c >> 5);
-        if (!TRON_DCHECK(r < W && c < H && w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) return;
+        const bool in_range = r < W && c < H && w < trail_bitmap_words(W, H);  // checked in release builds too: this is the rare path
+        if (!TRON_DCHECK(in_range, DBG_CELL_INDEX) || !in_range) return;
         // result unused -> RED.OR: no load the tick would have to wait for.  The reduction is performed in L2 and leaves a copy of the
         // line in this SM's L1 stale, so every READ of the bitmap bypasses L1 (__ldcg): a later tick of the same launch (step_many)
         // must see the bit (found by the differential fuzz: a missed collision let a list outgrow its capacity).
         atomicOr(bmp() + w, 1u << (c & 31));
     }
-    // the finished game's cold entries name the only bitmap words that can hold set bits: zero those (O(episode length), no extra state)
-    __device__ __forceinline__ void unmark_all() {
-        uint32_t* b = bmp();
-        const int nmax = max(n0, n1);
-        for (int k = kTrailHot; k < nmax; ++k) {
-            const uint32_t v = cold[k - kTrailHot];
-            if (k < n0) { const int w = (int)(v & 0x7Fu) * wpr() + (int)((v >> 13) & 7u); if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) b[w] = 0u; }
-            if (k < n1) { const int w = (int)((v >> 16) & 0x7Fu) * wpr() + (int)(v >> 29); if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) b[w] = 0u; }
-        }
+    // a finished game that had cold entries: zero its bitmap (16-byte stores; the cold area of a game is 16-byte aligned and both of
+    // its parts are multiples of 16 bytes).  Deliberately independent of the list contents.
+    __device__ __forceinline__ void clear_bitmap() {
+        uint4* b = (uint4*)bmp();
+        for (int q = 0; q < trail_bitmap_words(W, H) / 4; ++q) b[q] = make_uint4(0u, 0u, 0u, 0u);
     }
-
     __device__ __forceinline__ static unsigned short pack(int r, int c, bool slide) { return (unsigned short)((r & 0x7F) | (slide ? 0x80 : 0) | (c << 8)); }
 
     __device__ __forceinline__ void start(int a, int b) { n0 = a; n1 = b; fb = fs = 0xFFFFFFFFu; dirty = 0; }
@@ -115,14 +111,13 @@ struct TrailCells {
     __device__ __forceinline__ void clear() {  // fresh game: empty lists; the hot uint4s that held entries go back as placeholders
         const int used = min(kTrailHot, max(n0, n1));
         dirty |= (used > 0 ? 2u : 0u) | (used > 4 ? 4u : 0u) | (used > 8 ? 8u : 0u);
-        unmark_all();
+        if (max(n0, n1) > kTrailHot) clear_bitmap();
         n0 = n1 = 0; fb = fs = 0xFFFFFFFFu;
         blank();
     }
     // explicit reset: establishes every invariant whatever the memory held before (placeholders in all hot words, empty bitmap)
     __device__ __forceinline__ void reset_all() {
-        uint32_t* b = bmp();
-        for (int w = 0; w < trail_bitmap_words(W, H); ++w) b[w] = 0u;
+        clear_bitmap();
         n0 = n1 = 0; fb = fs = 0xFFFFFFFFu;
         blank();
         dirty = 0xEu;
@@ -143,7 +138,8 @@ struct TrailCells {
         uint32_t hit = hot_hit(r, c);
         if (max(n0, n1) > kTrailHot) {  // long episode: the cells of the list entries 12.. are in the bitmap
             const int w = r * wpr() + (c >> 5);
-            if (TRON_DCHECK(w < trail_bitmap_words(W, H), DBG_CELL_INDEX)) hit |= (__ldcg(bmp() + w) >> (c & 31)) & 1u;  // L2 read, see mark()
+            const bool in_range = w < trail_bitmap_words(W, H);
+            if (TRON_DCHECK(in_range, DBG_CELL_INDEX) && in_range) hit |= (__ldcg(bmp() + w) >> (c & 31)) & 1u;  // L2 read, see mark()
         }
         return hit ? TRON_TILE_P1_BODY : TRON_TILE_EMPTY;  // callers only test for EMPTY
     }
@@ -157,7 +153,7 @@ struct TrailCells {
         f = p2 ? ((f & 0x0000FFFFu) | (e << 16)) : ((f & 0xFFFF0000u) | e);
     }
     __device__ __forceinline__ void append(int owner, int k, uint32_t entry) {
-        if (!TRON_DCHECK(k < W * H, DBG_TRAIL_COUNT)) return;
+        if (!TRON_DCHECK(k < W * H, DBG_TRAIL_COUNT) || k >= W * H) return;
         const uint32_t v = entry << (16 * owner), keep = owner ? 0x0000FFFFu : 0xFFFF0000u;
         if (k < kTrailHot) {
 #pragma unroll
@@ -165,7 +161,8 @@ struct TrailCells {
                 if (w == k) hot[w] = (hot[w] & keep) | v;
             dirty |= 1u << (1 + (k >> 2));
         } else {
-            ((unsigned short*)(cold + (k - kTrailHot)))[owner] = (unsigned short)entry;
+            // one half of a list word: a 2-byte store in PTX, opaque to the compiler's type-based alias analysis (the word is read as 32 bits elsewhere)
+            asm volatile("st.global.u16 [%0], %1;" ::"l"((unsigned short*)(cold + (k - kTrailHot)) + owner), "h"((unsigned short)entry) : "memory");
             mark(entry);
         }
     }
@@ -174,7 +171,7 @@ struct TrailCells {
         if (fs == 0xFFFFFFFFu && n0 == n1 && (fb & 0xFFFFu) != 0xFFFFu && (fb >> 16) != 0xFFFFu) {
             // the common tick: both players leave one body, their lists are equally long -> the two entries are ONE list word
             const int k = n0;
-            if (TRON_DCHECK(k < W * H, DBG_TRAIL_COUNT)) {
+            if (TRON_DCHECK(k < W * H, DBG_TRAIL_COUNT) && k < W * H) {
                 if (k < kTrailHot) {
 #pragma unroll
                     for (int w = 0; w < kTrailHot; ++w)
@@ -228,7 +225,8 @@ __device__ __forceinline__ int free_neighbours(const TrailCells& g, const StepPa
         inb[k] = rr[k] >= 0 && cc[k] >= 0 && rr[k] < g.W && cc[k] < g.H;
         const int w = rr[k] * wpr + (cc[k] >> 5);
         wv[k] = 0u;
-        if (cold_on && inb[k] && TRON_DCHECK(w < trail_bitmap_words(g.W, g.H), DBG_CELL_INDEX)) wv[k] = __ldcg(b + w);  // L2 read, see mark()
+        const bool in_range = w >= 0 && w < trail_bitmap_words(g.W, g.H);
+        if (cold_on && inb[k] && TRON_DCHECK(in_range, DBG_CELL_INDEX) && in_range) wv[k] = __ldcg(b + w);  // L2 read, see mark()
     }
     int m = 0;
 #pragma unroll

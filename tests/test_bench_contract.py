@@ -54,8 +54,12 @@ def test_our_arm_config_legs():
     """the BASELINE config #3 / #4 / #5 legs of the default invocation (small headline so the test stays short)"""
     d = _run(["--steps", "2", "--warmup", "3", "--envs-per-gpu", "65536", "--ticks-per-step", "4", "--no-e2e", "--no-cpu-baseline", "--no-streams"], timeout=900)
     c = d["configs"]
-    assert set(c) == {"cfg3", "cfg4", "cfg5"}
+    assert set(c) == {"cfg3", "cfg4", "cfg5", "large_grid_fused_obs"}
     assert c["cfg5"]["value"] > 1e9 and c["cfg5"]["roofline"]["bound"] == "hbm" and 0 < c["cfg5"]["reset_fraction"] < 1
+    assert c["cfg5"]["step_many_16_ticks_per_launch"]["value"] > c["cfg5"]["value"]
+    assert [s["epsilon"] for s in c["cfg5"]["eps_greedy_streams"]] == [0.5, 0.1, 0.003]
+    assert all(s["value"] > 1e9 and s["mean_episode_ticks"] > 3 for s in c["cfg5"]["eps_greedy_streams"])
+    assert c["large_grid_fused_obs"]["value"] > 1e8 and 0.5 < c["large_grid_fused_obs"]["roofline"]["frac"] < 1.2
     for k in ("cfg3", "cfg4"):
         assert c[k]["value"] > 1e5 and set(c[k]["ms"]) >= {"q_forward", "env_replay", "learn"} and 0 < c[k]["env_replay_fraction_of_loop"] < 1
     assert "allreduce" in c["cfg4"]["ms"] and c["cfg4"]["learn_steps"] == 12

@@ -208,7 +208,9 @@ typedef struct tron_step_args {
     void* obs_terminal;   /* optional device buffer shaped and typed like `obs`: the rows of games that FINISHED in this call and were
                              auto-reset receive the observation of the finished game's last frame -- what DDQN.py:270-308 stores as
                              next_state of a terminal transition, while `obs` already shows the fresh game (ACKTR.py:309-310).  Rows
-                             of other games are left untouched.  TILE8 / BITS10 / BITS layouts, tron_step only.  NULL -> not written. */
+                             of other games are left untouched.  tron_step only.  Every layout; on TRAIL the observation rows of a group of
+                             games must fit the bulk-store kernel's shared-memory budget (200 KB; TRON_ERR_UNSUPPORTED otherwise, e.g.
+                             126x126 f32 with 4 planes).  NULL -> not written. */
     float* extra;         /* optional device [N,2,2] f32: per player {degree, weight_p} of the game `obs` shows (Game.get_multy,
                              tron/game.py:137-139) taken from slide_params; needs slide_params.  Written by tron_step,
                              tron_step_many (last tick), tron_observe and tron_reset_ex. */

@@ -1,5 +1,5 @@
-"""A short run of tools/fuzz_gpu.py: random configurations, CUDA vs oracle, bit for bit (5,214 configurations passed in the
-4-minute run recorded in DESIGN.md)."""
+"""A short run of tools/fuzz_gpu.py: random configurations, CUDA vs oracle, bit for bit (the long runs are recorded in
+profiles/r2_fuzz.log).  Seed 3 is the one whose 12th case exposed the trail-bitmap reset failure of round 2."""
 import os
 import sys
 
@@ -11,7 +11,7 @@ torch = pytest.importorskip("torch")
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 
 
-@pytest.mark.parametrize("seed", [11, 12])
+@pytest.mark.parametrize("seed", [3, 11, 12, 17, 29])
 def test_random_configurations(seed):
     import fuzz_gpu
     rng = np.random.default_rng(seed)

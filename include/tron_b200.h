@@ -232,7 +232,8 @@ int tron_state_offsets(int n_envs, int width, int height, int layout, size_t* gr
 enum {
     TRON_OPT_SPARSE_MIN_CELLS = 1,
     TRON_OPT_TILE_BYTES = 2, /* shared-memory budget of one tile of games in the generic-size fused kernel (default 18432) */
-    TRON_OPT_ENCODE_VARIANT = 3, /* experiments: 8 = per-plane observation store schedule on 10x10 boards instead of the linear one (0 = default) */
+    TRON_OPT_ENCODE_VARIANT = 3, /* experiments (bit mask, 0 = default): 8 = per-plane observation store schedule on 10x10 boards instead of
+                                     the linear one; 32 = element-store observation kernel on the trail layout instead of the bulk-store one */
     TRON_OPT_BITS_CTAS_PER_SM = 4, /* resident CTAs per SM of the fused bit-plane kernels (capped by padding the dynamic shared memory).
                                      0 = default: 4 for the two-plane kernels, 5 with the slide plane -- these kernels are write
                                      streams and FEWER concurrent streams per SM than the register limit of 8 run faster on B200

@@ -111,6 +111,18 @@ def test_trail_step_many_sees_its_own_bitmap_updates(W, slide):
     assert longest > 20  # trails well beyond the 12 entries kept in the hot words
 
 
+@pytest.mark.parametrize("W,slide", [(8, abi.SLIDE_ICE), (10, abi.SLIDE_TEMPER)])
+def test_trail_long_trails_with_slide_modes_tick_by_tick(W, slide):
+    """the trigger of round 2's reset failure (tools/long_trail_case.py): 20,000 games under the free-neighbour policy with a slide
+    mode -- lists of unequal length growing past the hot words, games with cold entries being reset from tick ~10 on"""
+    N = 20000
+    g, o = make_pair(N, W, W, seed=3, slide_mode=slide, slide_rate=0.15, policy=abi.POLICY_FREE_EPS, policy_epsilon=0.0, **KW)
+    g.reset(); o.reset()
+    for t in range(40):
+        assert_same_step(g.step(), o.step(), "tick %d" % t)
+    assert_same_state(g, o)
+
+
 def test_trail_import_export_and_cross_layout():
     N, W = 700, 12
     a = GpuEnvNumpy(N, W, W, seed=5, **KW)

@@ -17,12 +17,12 @@
 // Only episodes longer than 12 ticks touch the cold area, which holds two things per game: the list words >= 12 (write-only for
 // the tick: they give export / observation rendering the owner and slide flag of every cell) and an OCCUPANCY BITMAP over the
 // interior cells with one bit per cell that a cold entry names.  "Is this cell free?" for a long game is then the 12-word register
-// scan plus ONE 4-byte probe of the bitmap instead of a walk over the whole list (round 2 walked it: every probe of a long
-// game cost O(episode length) loads, the epsilon-greedy streams ran at a ninth of the short-episode rate); a reset of a game that had cold entries zeroes its
-// bitmap (512 B at 64x64, 16-byte stores).  Unused entries of the hot words hold the impossible key 0xFFFF (see
-// TrailCells), which makes "is this cell free?" a branch-free packed-minimum over the words (VIMNMX3.U16x2, 1.5 instructions per
-// list word); the kernel is instruction-issue-bound, not bandwidth-bound (profiles/r2_step_trail_64x64_2M.json: issue active 75 %,
-// DRAM 29 %), so instruction count is what the layout and these tricks buy.
+// scan plus ONE 4-byte probe of the bitmap instead of a walk over the whole list (round 2 first walked it: every probe of a long
+// game cost O(episode length) loads, the epsilon-greedy streams ran at a ninth of the short-episode rate); a reset of a game that
+// had cold entries zeroes its bitmap (512 B at 64x64, 16-byte stores).  Unused entries of the hot words hold the impossible key
+// 0xFFFF (see TrailCells), which makes "is this cell free?" a branch-free packed-minimum over the words (VIMNMX3.U16x2, 1.5
+// instructions per list word); the kernel is instruction-issue-bound, not bandwidth-bound (profiles/r2_step_trail_64x64_2M.json:
+// issue active 74 %, DRAM 19 %), so instruction count is what the layout and these tricks buy.
 #include <algorithm>
 
 #include "launch.h"
